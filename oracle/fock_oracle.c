@@ -1,0 +1,625 @@
+/*
+ * oracle/fock_oracle.c -- CPU restatement of fock-rs's ERI + Fock-build path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under fock_rs_b200/ (the product) may link, import
+ * or call this file.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` legs use it, and there only as the checker / the timed CPU baseline.
+ *
+ * The reference is Rust and cannot be compiled in this image (no cargo/rustc), so this
+ * is a restatement, recursion for recursion, of the reference's own source; every
+ * function cites the file:line it follows (paths relative to /root/reference).
+ *
+ * Parity pinning: the reference's only numeric known-answer test on this path is the
+ * `hermite_expansion` doctest (basis/src/utils.rs:24), which this file reproduces
+ * bit-exactly (tests/test_oracle.py).  ERIs / G / energies are "parity unpinned by the
+ * reference's own tests": they are pinned by this source restatement plus the
+ * independent survey probe values recorded in SURVEY.md App. B.
+ *
+ * Two evaluators are provided for the contracted ERI:
+ *   - oracle_eri()       the reference's un-memoised recursion, loop for loop (slow; this
+ *                        is what the CPU baseline times);
+ *   - oracle_eri_fast()  the same formulas with the E and R recursions tabulated once per
+ *                        primitive pair / quartet (used for large parity cases; checked
+ *                        against oracle_eri() in tests/test_oracle.py).
+ *
+ * Flags select the reference-faithful quirks (default 0 = faithful):
+ *   ORACLE_BOYS_EXACT  exact Boys function instead of the LUT + downward recursion (F1)
+ *   ORACLE_FIX_R       restore the (t-1) factor in coulomb_auxiliary's x branch   (F2)
+ *   ORACLE_NO_CUT      disable the 1e-6 estimate cut in the tensor build          (F3)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORACLE_BOYS_EXACT 1
+#define ORACLE_FIX_R 2
+#define ORACLE_NO_CUT 4
+
+#define PI 3.14159265358979323846264338327950288 /* std::f64::consts::PI */
+#define FRAC_2_PI 0.636619772367581343075535053490057448 /* std::f64::consts::FRAC_2_PI */
+#define TAU 6.28318530717958647692528676655900577 /* std::f64::consts::TAU */
+
+/* Same SoA the C ABI takes (include/fock_b200.h: fock_basis). */
+typedef struct {
+    int32_t n_basis;
+    const double *center;       /* [N][3] bohr */
+    const int32_t *angular;     /* [N][3] */
+    const int32_t *prim_offset; /* [N+1] */
+    const double *exponent;     /* [nprim] */
+    const double *coefficient;  /* [nprim], norm folded in */
+} oracle_basis;
+
+/* f64::powi -> llvm.powi.f64.i32 -> compiler-rt __powidf2 (published algorithm:
+ * square-and-multiply from the low bit, reciprocal at the end for negative exponents). */
+static double powi(double a, int b) {
+    const int recip = b < 0;
+    double r = 1.0;
+    while (1) {
+        if (b & 1) r *= a;
+        b /= 2;
+        if (b == 0) break;
+        a *= a;
+    }
+    return recip ? 1.0 / r : r;
+}
+
+/* ------------------------------------------------------------------ Boys function */
+
+static const double BOYS_LUT[200] = {
+#include "boys_lut.inc"
+};
+
+/* boys/src/lib.rs:5-10 */
+static uint32_t double_factorial(uint32_t n) {
+    if (n == 0) return 1;
+    uint32_t prod = 1;
+    for (uint32_t k = 2 - n % 2; k <= n; k += 2) prod *= k;
+    return prod;
+}
+
+/* boys/src/lib.rs:58-81 with _boys_impl :13-21 and the constants :23-26
+ * (DT=0.15, MAX_TABULATED_T=30, MAX_TABULATED_N=10, N=200).  Returns NaN for n>10 where
+ * the reference panics. */
+double oracle_boys(double t, int n) {
+    if (n > 10) return NAN;
+    if (fabs(t) < 1e-16) {
+        return 1.0 / (double)(2 * n + 1);
+    } else if (fabs(t) >= 30.0) {
+        uint32_t two_n = (uint32_t)(2 * n);
+        uint32_t arg = two_n == 0 ? 0 : two_n - 1; /* saturating_sub(1) */
+        return (double)double_factorial(arg) * (1.0 / powi(2.0, n + 1)) * sqrt(PI * powi(t, -2 * n - 1));
+    } else {
+        double index_f = 200.0 * t / 30.0;
+        double lower = floor(index_f);
+        double upper = ceil(index_f);
+        double int_t = index_f - lower;
+        size_t lo = (size_t)lower;
+        size_t up = (size_t)upper;
+        if (up > 199) up = 199;
+        double curr = int_t * BOYS_LUT[up] + (1.0 - int_t) * BOYS_LUT[lo];
+        double exp_mt = exp(-t);
+        int curr_n = 10;
+        while (curr_n > n) {
+            curr = (2.0 * t * curr + exp_mt) / (double)(2 * curr_n - 1);
+            curr_n -= 1;
+        }
+        return curr;
+    }
+}
+
+/* Accurate Boys function (opt-in "accurate" mode; not in the reference).
+ * F_n(T) = exp(-T) * sum_k (2T)^k / ((2n+1)(2n+3)...(2n+2k+1)) for T < 50 (all terms
+ * positive), asymptotic (2n-1)!!/2^(n+1) sqrt(pi/T^(2n+1)) beyond (error < exp(-50)). */
+double oracle_boys_exact(double t, int n) {
+    if (t < 0) t = -t;
+    if (t < 50.0) {
+        double term = 1.0 / (double)(2 * n + 1);
+        double sum = term;
+        for (int k = 1; k < 400; ++k) {
+            term *= 2.0 * t / (double)(2 * n + 2 * k + 1);
+            sum += term;
+            if (term < 1e-18 * sum) break;
+        }
+        return exp(-t) * sum;
+    }
+    double df = 1.0;
+    for (int k = 2 * n - 1; k > 1; k -= 2) df *= (double)k;
+    return df / pow(2.0, n + 1) * sqrt(PI / pow(t, 2 * n + 1));
+}
+
+static double boys_sel(double t, int n, int flags) {
+    return (flags & ORACLE_BOYS_EXACT) ? oracle_boys_exact(t, n) : oracle_boys(t, n);
+}
+
+/* ------------------------------------------------------------------ MD recursions */
+
+/* basis/src/utils.rs:33-50 */
+double oracle_hermite_expansion(int i, int j, int t, double dist, double a, double b) {
+    double p = a + b;
+    double q = a * b / p;
+    if (t < 0 || t > i + j) {
+        return 0.0;
+    } else if (i == j && j == t && t == 0) {
+        return exp(-q * powi(dist, 2));
+    } else if (j == 0) {
+        return (1.0 / (2.0 * p)) * oracle_hermite_expansion(i - 1, j, t - 1, dist, a, b) -
+               (q * dist / a) * oracle_hermite_expansion(i - 1, j, t, dist, a, b) +
+               (double)(t + 1) * oracle_hermite_expansion(i - 1, j, t + 1, dist, a, b);
+    } else {
+        return (1.0 / (2.0 * p)) * oracle_hermite_expansion(i, j - 1, t - 1, dist, a, b) +
+               (q * dist / b) * oracle_hermite_expansion(i, j - 1, t, dist, a, b) +
+               (double)(t + 1) * oracle_hermite_expansion(i, j - 1, t + 1, dist, a, b);
+    }
+}
+
+/* basis/src/utils.rs:73-106.  Note the x branch (:98-105) has no (t-1) factor (F2). */
+double oracle_coulomb_auxiliary(int t, int u, int v, int n, double p, const double diff[3], double dist_sq,
+                                int flags) {
+    if (t == u && u == v && v == 0) {
+        return powi(-2.0 * p, n) * boys_sel(p * dist_sq, n, flags);
+    } else if (t == u && u == 0) {
+        return diff[2] * oracle_coulomb_auxiliary(t, u, v - 1, n + 1, p, diff, dist_sq, flags) +
+               (v > 1 ? (double)(v - 1) * oracle_coulomb_auxiliary(t, u, v - 2, n + 1, p, diff, dist_sq, flags)
+                      : 0.0);
+    } else if (t == 0) {
+        return diff[1] * oracle_coulomb_auxiliary(t, u - 1, v, n + 1, p, diff, dist_sq, flags) +
+               (u > 1 ? (double)(u - 1) * oracle_coulomb_auxiliary(t, u - 2, v, n + 1, p, diff, dist_sq, flags)
+                      : 0.0);
+    } else {
+        double second = 0.0;
+        if (t > 1) {
+            second = oracle_coulomb_auxiliary(t - 2, u, v, n + 1, p, diff, dist_sq, flags);
+            if (flags & ORACLE_FIX_R) second = (double)(t - 1) * second;
+        }
+        return diff[0] * oracle_coulomb_auxiliary(t - 1, u, v, n + 1, p, diff, dist_sq, flags) + second;
+    }
+}
+
+/* ------------------------------------------------------------------ primitives */
+
+/* basis/src/primitives.rs:19-27 (integer products in i32, as in the reference) */
+double oracle_norm(int i, int j, int k, double alpha) {
+    int32_t pi_ = 1, pj = 1, pk = 1;
+    for (int m = i + 1; m <= 2 * i; ++m) pi_ *= m;
+    for (int m = j + 1; m <= 2 * j; ++m) pj *= m;
+    for (int m = k + 1; m <= 2 * k; ++m) pk *= m;
+    return sqrt(sqrt(powi(FRAC_2_PI * alpha, 3))) * sqrt(powi(8.0 * alpha, i + j + k) / (double)(pi_ * pj * pk));
+}
+
+typedef struct {
+    int ang[3];
+    double e;
+} prim_t;
+
+/* basis/src/contracted_gaussian.rs:140-205 */
+static double prim_eri(const prim_t *A, const prim_t *B, const prim_t *C, const prim_t *D, const double diff_ab[3],
+                       const double diff_cd[3], const double comp_diff[3], double comp_dist_sq, int flags) {
+    const int l1 = A->ang[0], m1 = A->ang[1], n1 = A->ang[2];
+    const int l2 = B->ang[0], m2 = B->ang[1], n2 = B->ang[2];
+    const int l3 = C->ang[0], m3 = C->ang[1], n3 = C->ang[2];
+    const int l4 = D->ang[0], m4 = D->ang[1], n4 = D->ang[2];
+    const double a = A->e, b = B->e, c = C->e, d = D->e;
+    double p = a + b;
+    double q = c + d;
+    double alpha = p * q / (p + q);
+    double sum = 0.0;
+    for (int t1 = 0; t1 <= l1 + l2; ++t1) {
+        double e1 = oracle_hermite_expansion(l1, l2, t1, diff_ab[0], a, b);
+        for (int u1 = 0; u1 <= m1 + m2; ++u1) {
+            double e2 = oracle_hermite_expansion(m1, m2, u1, diff_ab[1], a, b);
+            for (int v1 = 0; v1 <= n1 + n2; ++v1) {
+                double e3 = oracle_hermite_expansion(n1, n2, v1, diff_ab[2], a, b);
+                for (int t2 = 0; t2 <= l3 + l4; ++t2) {
+                    double e4 = oracle_hermite_expansion(l3, l4, t2, diff_cd[0], c, d);
+                    for (int u2 = 0; u2 <= m3 + m4; ++u2) {
+                        double e5 = oracle_hermite_expansion(m3, m4, u2, diff_cd[1], c, d);
+                        for (int v2 = 0; v2 <= n3 + n4; ++v2) {
+                            double e6 = oracle_hermite_expansion(n3, n4, v2, diff_cd[2], c, d);
+                            sum += e1 * e2 * e3 * e4 * e5 * e6 *
+                                   oracle_coulomb_auxiliary(t1 + t2, u1 + u2, v1 + v2, 0, alpha, comp_diff,
+                                                            comp_dist_sq, flags) *
+                                   (((t2 + u2 + v2) % 2 == 0) ? 1.0 : -1.0);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    return 2.0 * sqrt(powi(PI, 5)) * (1.0 / (p * q * sqrt(p + q))) * sum;
+}
+
+/* basis/src/primitives.rs:63-74 */
+static void product_center(double ae, const double *apos, double be, const double *bpos, double out[3]) {
+    for (int k = 0; k < 3; ++k) out[k] = (ae * apos[k] + be * bpos[k]) / (ae + be);
+}
+
+/* basis/src/contracted_gaussian.rs:264-318 */
+double oracle_eri(const oracle_basis *bs, int ia, int ib, int ic, int id, int flags) {
+    const double *ap = bs->center + 3 * ia, *bp = bs->center + 3 * ib;
+    const double *cp = bs->center + 3 * ic, *dp = bs->center + 3 * id;
+    double diff_ab[3], diff_cd[3];
+    for (int k = 0; k < 3; ++k) {
+        diff_ab[k] = bp[k] - ap[k];
+        diff_cd[k] = dp[k] - cp[k];
+    }
+    prim_t A, B, C, D;
+    for (int k = 0; k < 3; ++k) {
+        A.ang[k] = bs->angular[3 * ia + k];
+        B.ang[k] = bs->angular[3 * ib + k];
+        C.ang[k] = bs->angular[3 * ic + k];
+        D.ang[k] = bs->angular[3 * id + k];
+    }
+    double sum = 0.0;
+    for (int i = bs->prim_offset[ia]; i < bs->prim_offset[ia + 1]; ++i) {
+        for (int j = bs->prim_offset[ib]; j < bs->prim_offset[ib + 1]; ++j) {
+            double comp_ab[3];
+            product_center(bs->exponent[i], ap, bs->exponent[j], bp, comp_ab);
+            for (int k = bs->prim_offset[ic]; k < bs->prim_offset[ic + 1]; ++k) {
+                for (int l = bs->prim_offset[id]; l < bs->prim_offset[id + 1]; ++l) {
+                    double comp_cd[3], comp_diff[3];
+                    product_center(bs->exponent[k], cp, bs->exponent[l], dp, comp_cd);
+                    for (int m = 0; m < 3; ++m) comp_diff[m] = comp_cd[m] - comp_ab[m];
+                    double dist_sq =
+                        comp_diff[0] * comp_diff[0] + comp_diff[1] * comp_diff[1] + comp_diff[2] * comp_diff[2];
+                    A.e = bs->exponent[i];
+                    B.e = bs->exponent[j];
+                    C.e = bs->exponent[k];
+                    D.e = bs->exponent[l];
+                    sum += bs->coefficient[i] * bs->coefficient[j] * bs->coefficient[k] * bs->coefficient[l] *
+                           prim_eri(&A, &B, &C, &D, diff_ab, diff_cd, comp_diff, dist_sq, flags);
+                }
+            }
+        }
+    }
+    return sum;
+}
+
+/* ---------------------------------------------------------------- tabulated evaluator
+ * Same formulas as above (same recursion relations, same branch order in R, same Boys),
+ * but each E row and the R table are built once instead of re-expanded per term.  Values
+ * agree with oracle_eri() to rounding (tests/test_oracle.py asserts <= 1e-13). */
+
+#define LMAX1 5   /* per-function l <= 4 */
+#define TMAX 9    /* i+j <= 8 */
+#define RDIM 11   /* t,u,v,n <= 10 (Boys order limit of the reference) */
+
+/* E[i][j][t] for i<=la, j<=lb by the reference's recursion: lower i while j==0, else lower j. */
+static void e_table(int la, int lb, double dist, double a, double b, double E[LMAX1][LMAX1][TMAX + 2]) {
+    double p = a + b, q = a * b / p;
+    memset(E, 0, sizeof(double) * LMAX1 * LMAX1 * (TMAX + 2));
+    E[0][0][0] = exp(-q * powi(dist, 2));
+    for (int i = 1; i <= la; ++i)
+        for (int t = 0; t <= i; ++t)
+            E[i][0][t] = (1.0 / (2.0 * p)) * (t > 0 ? E[i - 1][0][t - 1] : 0.0) - (q * dist / a) * E[i - 1][0][t] +
+                         (double)(t + 1) * E[i - 1][0][t + 1];
+    for (int i = 0; i <= la; ++i)
+        for (int j = 1; j <= lb; ++j)
+            for (int t = 0; t <= i + j; ++t)
+                E[i][j][t] = (1.0 / (2.0 * p)) * (t > 0 ? E[i][j - 1][t - 1] : 0.0) +
+                             (q * dist / b) * E[i][j - 1][t] + (double)(t + 1) * E[i][j - 1][t + 1];
+}
+
+/* R[t][u][v] (n=0) for t<=T,u<=U,v<=V, built in the reference's reduction order:
+ * v first (t=u=0), then u (t=0), then t -- the x step without the (t-1) factor unless FIX_R. */
+static void r_table(int T, int U, int V, double alpha, const double diff[3], double dist_sq, int flags,
+                    double R0[TMAX][TMAX][TMAX]) {
+    static _Thread_local double R[RDIM][TMAX][TMAX][TMAX]; /* [n][t][u][v] */
+    int L = T + U + V;
+    if (L > 10) L = 10;
+    for (int n = 0; n <= L; ++n) R[n][0][0][0] = powi(-2.0 * alpha, n) * boys_sel(alpha * dist_sq, n, flags);
+    for (int v = 1; v <= V; ++v)
+        for (int n = 0; n + v <= L; ++n)
+            R[n][0][0][v] = diff[2] * R[n + 1][0][0][v - 1] + (v > 1 ? (double)(v - 1) * R[n + 1][0][0][v - 2] : 0.0);
+    for (int u = 1; u <= U; ++u)
+        for (int v = 0; v <= V; ++v)
+            for (int n = 0; n + u + v <= L; ++n)
+                R[n][0][u][v] =
+                    diff[1] * R[n + 1][0][u - 1][v] + (u > 1 ? (double)(u - 1) * R[n + 1][0][u - 2][v] : 0.0);
+    for (int t = 1; t <= T; ++t)
+        for (int u = 0; u <= U; ++u)
+            for (int v = 0; v <= V; ++v)
+                for (int n = 0; n + t + u + v <= L; ++n) {
+                    double second = 0.0;
+                    if (t > 1) {
+                        second = R[n + 1][t - 2][u][v];
+                        if (flags & ORACLE_FIX_R) second = (double)(t - 1) * second;
+                    }
+                    R[n][t][u][v] = diff[0] * R[n + 1][t - 1][u][v] + second;
+                }
+    for (int t = 0; t <= T; ++t)
+        for (int u = 0; u <= U; ++u)
+            for (int v = 0; v <= V; ++v) R0[t][u][v] = R[0][t][u][v];
+}
+
+double oracle_eri_fast(const oracle_basis *bs, int ia, int ib, int ic, int id, int flags) {
+    const double *ap = bs->center + 3 * ia, *bp = bs->center + 3 * ib;
+    const double *cp = bs->center + 3 * ic, *dp = bs->center + 3 * id;
+    const int32_t *la = bs->angular + 3 * ia, *lb = bs->angular + 3 * ib;
+    const int32_t *lc = bs->angular + 3 * ic, *ld = bs->angular + 3 * id;
+    double diff_ab[3], diff_cd[3];
+    for (int k = 0; k < 3; ++k) {
+        diff_ab[k] = bp[k] - ap[k];
+        diff_cd[k] = dp[k] - cp[k];
+    }
+    int T[3];
+    for (int k = 0; k < 3; ++k) T[k] = la[k] + lb[k] + lc[k] + ld[k];
+    if (T[0] + T[1] + T[2] > 10) return NAN;
+    double Eab[3][LMAX1][LMAX1][TMAX + 2], Ecd[3][LMAX1][LMAX1][TMAX + 2];
+    double R0[TMAX][TMAX][TMAX];
+    double sum = 0.0;
+    for (int i = bs->prim_offset[ia]; i < bs->prim_offset[ia + 1]; ++i) {
+        for (int j = bs->prim_offset[ib]; j < bs->prim_offset[ib + 1]; ++j) {
+            double a = bs->exponent[i], b = bs->exponent[j];
+            double comp_ab[3];
+            product_center(a, ap, b, bp, comp_ab);
+            for (int k = 0; k < 3; ++k) e_table(la[k], lb[k], diff_ab[k], a, b, Eab[k]);
+            for (int k = bs->prim_offset[ic]; k < bs->prim_offset[ic + 1]; ++k) {
+                for (int l = bs->prim_offset[id]; l < bs->prim_offset[id + 1]; ++l) {
+                    double c = bs->exponent[k], d = bs->exponent[l];
+                    double comp_cd[3], comp_diff[3];
+                    product_center(c, cp, d, dp, comp_cd);
+                    for (int m = 0; m < 3; ++m) comp_diff[m] = comp_cd[m] - comp_ab[m];
+                    double dist_sq =
+                        comp_diff[0] * comp_diff[0] + comp_diff[1] * comp_diff[1] + comp_diff[2] * comp_diff[2];
+                    for (int m = 0; m < 3; ++m) e_table(lc[m], ld[m], diff_cd[m], c, d, Ecd[m]);
+                    double p = a + b, q = c + d, alpha = p * q / (p + q);
+                    r_table(T[0], T[1], T[2], alpha, comp_diff, dist_sq, flags, R0);
+                    double s = 0.0;
+                    for (int t1 = 0; t1 <= la[0] + lb[0]; ++t1)
+                        for (int u1 = 0; u1 <= la[1] + lb[1]; ++u1)
+                            for (int v1 = 0; v1 <= la[2] + lb[2]; ++v1) {
+                                double eab = Eab[0][la[0]][lb[0]][t1] * Eab[1][la[1]][lb[1]][u1] *
+                                             Eab[2][la[2]][lb[2]][v1];
+                                for (int t2 = 0; t2 <= lc[0] + ld[0]; ++t2)
+                                    for (int u2 = 0; u2 <= lc[1] + ld[1]; ++u2)
+                                        for (int v2 = 0; v2 <= lc[2] + ld[2]; ++v2)
+                                            s += eab * Ecd[0][lc[0]][ld[0]][t2] * Ecd[1][lc[1]][ld[1]][u2] *
+                                                 Ecd[2][lc[2]][ld[2]][v2] * R0[t1 + t2][u1 + u2][v1 + v2] *
+                                                 (((t2 + u2 + v2) % 2 == 0) ? 1.0 : -1.0);
+                            }
+                    sum += bs->coefficient[i] * bs->coefficient[j] * bs->coefficient[k] * bs->coefficient[l] * 2.0 *
+                           sqrt(powi(PI, 5)) * (1.0 / (p * q * sqrt(p + q))) * s;
+                }
+            }
+        }
+    }
+    return sum;
+}
+
+static double eri_sel(const oracle_basis *bs, int a, int b, int c, int d, int flags, int fast) {
+    return fast ? oracle_eri_fast(bs, a, b, c, d, flags) : oracle_eri(bs, a, b, c, d, flags);
+}
+
+/* ------------------------------------------------------------------ tensor build */
+
+static inline size_t tri(size_t x, size_t y) { return x * (x + 1) / 2 + y; } /* x >= y */
+
+/* Canonical 8-fold packed position; basis/src/electron_tensor.rs:37-51 (correct_order).  The
+ * reference stores at w*N^3+z*N^2+y*N+x of a dense N^4 array (:53-55); only canonical slots
+ * are ever filled, so the packed triangular-of-triangular index holds the same information. */
+size_t oracle_packed_index(size_t x, size_t y, size_t z, size_t w) {
+    if (x < y) { size_t s = x; x = y; y = s; }
+    if (z < w) { size_t s = z; z = w; w = s; }
+    size_t xy = tri(x, y), zw = tri(z, w);
+    return xy >= zw ? tri(xy, zw) : tri(zw, xy);
+}
+
+size_t oracle_packed_len(size_t n) {
+    size_t p = n * (n + 1) / 2;
+    return p * (p + 1) / 2;
+}
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* basis/src/electron_tensor.rs:81-176: diagonal pass (:90-101), then every other unique
+ * integral = estimate > 1e-6 ? ERI : 0.0 with estimate = sqrt(diag_ij*diag_kl) (:129-158).
+ * The reference visits each unique off-diagonal integral twice, from two rayon tasks, with
+ * the two argument orders (xy|zw) / (zw|xy) and keeps whichever lands first (F4, ulp-level
+ * nondeterminism).  This restatement evaluates each once, bra = the larger pair index, the
+ * order the canonical visit uses.  Parallel over the canonical row like the reference's
+ * single into_par_iter (:113).  `packed` has oracle_packed_len(N) entries.
+ * Returns the number of off-diagonal integrals actually evaluated. */
+int64_t oracle_from_basis_packed(const oracle_basis *bs, int flags, int fast, double *packed) {
+    const size_t n = (size_t)bs->n_basis;
+    const size_t np = n * (n + 1) / 2;
+    int32_t *px = (int32_t *)malloc(sizeof(int32_t) * np), *py = (int32_t *)malloc(sizeof(int32_t) * np);
+    for (size_t x = 0; x < n; ++x)
+        for (size_t y = 0; y <= x; ++y) {
+            px[tri(x, y)] = (int32_t)x;
+            py[tri(x, y)] = (int32_t)y;
+        }
+    double *diag = (double *)malloc(sizeof(double) * np);
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t xy = 0; xy < (int64_t)np; ++xy) {
+        diag[xy] = eri_sel(bs, px[xy], py[xy], px[xy], py[xy], flags, fast);
+        packed[tri(xy, xy)] = diag[xy];
+    }
+    int64_t evaluated = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : evaluated)
+    for (int64_t xy = (int64_t)np - 1; xy >= 0; --xy) {
+        for (int64_t zw = 0; zw < xy; ++zw) {
+            double estimate = sqrt(diag[xy] * diag[zw]);
+            double v = 0.0;
+            if ((flags & ORACLE_NO_CUT) || estimate > 1e-6) {
+                v = eri_sel(bs, px[xy], py[xy], px[zw], py[zw], flags, fast);
+                evaluated += 1;
+            }
+            packed[tri(xy, zw)] = v;
+        }
+    }
+    free(px);
+    free(py);
+    free(diag);
+    return evaluated;
+}
+
+/* Bounded sample of the tensor build for CPU-baseline timing: evaluates canonical rows
+ * xy = row_start, row_start+row_stride, ... (each row: all zw < xy that survive the cut),
+ * results discarded except a checksum.  `diag` must hold the np diagonal integrals.
+ * Returns evaluated count; *checksum gets the sum. */
+int64_t oracle_sample_rows(const oracle_basis *bs, int flags, int fast, const double *diag, int64_t row_start,
+                           int64_t row_stride, int64_t max_rows, double *checksum) {
+    const size_t n = (size_t)bs->n_basis;
+    const size_t np = n * (n + 1) / 2;
+    int32_t *px = (int32_t *)malloc(sizeof(int32_t) * np), *py = (int32_t *)malloc(sizeof(int32_t) * np);
+    for (size_t x = 0; x < n; ++x)
+        for (size_t y = 0; y <= x; ++y) {
+            px[tri(x, y)] = (int32_t)x;
+            py[tri(x, y)] = (int32_t)y;
+        }
+    int64_t evaluated = 0;
+    double cs = 0.0;
+    int64_t nrows = 0;
+    for (int64_t xy = row_start; xy < (int64_t)np && nrows < max_rows; xy += row_stride) ++nrows;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : evaluated, cs)
+    for (int64_t r = 0; r < nrows; ++r) {
+        int64_t xy = row_start + r * row_stride;
+        for (int64_t zw = 0; zw < xy; ++zw) {
+            double estimate = sqrt(diag[xy] * diag[zw]);
+            if ((flags & ORACLE_NO_CUT) || estimate > 1e-6) {
+                cs += eri_sel(bs, px[xy], py[xy], px[zw], py[zw], flags, fast);
+                evaluated += 1;
+            }
+        }
+    }
+    free(px);
+    free(py);
+    *checksum = cs;
+    return evaluated;
+}
+
+void oracle_diagonal(const oracle_basis *bs, int flags, int fast, double *diag) {
+    const size_t n = (size_t)bs->n_basis;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int64_t x = 0; x < (int64_t)n; ++x)
+        for (int64_t y = 0; y <= x; ++y) diag[tri(x, y)] = eri_sel(bs, x, y, x, y, flags, fast);
+}
+
+/* ------------------------------------------------------------------ Fock build */
+
+/* scf/src/lib.rs:167-185 inside utils::hermitian (scf/src/utils.rs:25-28):
+ *   electron_terms[j,i,y,x] = multi[(i,j,x,y)] - 0.5*multi[(i,x,j,y)]
+ *   G_ij (i<=j) = sum_y ( sum_x D[(x,y)] * electron_terms[j,i,y,x] ),  G_ji = G_ij.
+ * D and G are column-major N x N (nalgebra DMatrix): D[(x,y)] = D[x + y*N].
+ * Same summation order as the reference (x inner, y outer).  `parallel`!=0 spreads (i,j)
+ * over OpenMP threads (the reference loop is serial). */
+void oracle_build_g(const double *packed, int n_basis, const double *D, double *G, int parallel) {
+    const int n = n_basis;
+#pragma omp parallel for schedule(dynamic, 1) if (parallel)
+    for (int j = 0; j < n; ++j) {
+        for (int i = 0; i <= j; ++i) {
+            double acc = 0.0;
+            for (int y = 0; y < n; ++y) {
+                double inner = 0.0;
+                for (int x = 0; x < n; ++x) {
+                    double term = packed[oracle_packed_index(i, j, x, y)] - 0.5 * packed[oracle_packed_index(i, x, j, y)];
+                    inner = inner + D[x + (size_t)y * n] * term;
+                }
+                acc = acc + inner;
+            }
+            G[i + (size_t)j * n] = acc;
+            G[j + (size_t)i * n] = acc;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ one-electron integrals
+ * (off the hot path; needed so the test harness can run an SCF).                          */
+
+static double prim_overlap(const int la[3], double a, const int lb[3], double b, const double diff[3]) {
+    /* basis/src/contracted_gaussian.rs:51-69 */
+    return oracle_hermite_expansion(la[0], lb[0], 0, diff[0], a, b) *
+           oracle_hermite_expansion(la[1], lb[1], 0, diff[1], a, b) *
+           oracle_hermite_expansion(la[2], lb[2], 0, diff[2], a, b) * sqrt(powi(PI / (a + b), 3));
+}
+
+static double overlap_step(const int la[3], double a, const int lb[3], double b, const double diff[3], int di,
+                           int dj, int dk) {
+    /* GaussianPrimitive::_add_ijk, basis/src/contracted_gaussian.rs:38-48 */
+    int s[3] = {lb[0] + di, lb[1] + dj, lb[2] + dk};
+    return prim_overlap(la, a, s, b, diff);
+}
+
+static double prim_kinetic(const int la[3], double a, const int lb[3], double b, const double diff[3]) {
+    /* basis/src/contracted_gaussian.rs:72-95 */
+    const int l2 = lb[0], m2 = lb[1], n2 = lb[2];
+    double term0 = b * (double)(2 * (l2 + m2 + n2) + 3) * prim_overlap(la, a, lb, b, diff);
+    double term1 = -2.0 * powi(b, 2) *
+                   (overlap_step(la, a, lb, b, diff, 2, 0, 0) + overlap_step(la, a, lb, b, diff, 0, 2, 0) +
+                    overlap_step(la, a, lb, b, diff, 0, 0, 2));
+    double term2 = -0.5 * ((double)(l2 * (l2 - 1)) * overlap_step(la, a, lb, b, diff, -2, 0, 0) +
+                           (double)(m2 * (m2 - 1)) * overlap_step(la, a, lb, b, diff, 0, -2, 0) +
+                           (double)(n2 * (n2 - 1)) * overlap_step(la, a, lb, b, diff, 0, 0, -2));
+    return term0 + term1 + term2;
+}
+
+static double prim_nuclear(const int la[3], double a, const int lb[3], double b, const double diff[3],
+                           const double prod_center[3], const double npos[3], double charge, int flags) {
+    /* basis/src/contracted_gaussian.rs:98-137 */
+    double p = a + b;
+    double dn[3] = {npos[0] - prod_center[0], npos[1] - prod_center[1], npos[2] - prod_center[2]};
+    double dsq = dn[0] * dn[0] + dn[1] * dn[1] + dn[2] * dn[2];
+    double sum = 0.0;
+    for (int t = 0; t <= la[0] + lb[0]; ++t) {
+        double e1 = oracle_hermite_expansion(la[0], lb[0], t, diff[0], a, b);
+        for (int u = 0; u <= la[1] + lb[1]; ++u) {
+            double e2 = oracle_hermite_expansion(la[1], lb[1], u, diff[1], a, b);
+            for (int v = 0; v <= la[2] + lb[2]; ++v) {
+                double e3 = oracle_hermite_expansion(la[2], lb[2], v, diff[2], a, b);
+                sum += e1 * e2 * e3 * oracle_coulomb_auxiliary(t, u, v, 0, p, dn, dsq, flags);
+            }
+        }
+    }
+    return -charge * TAU / p * sum;
+}
+
+/* S, T, V (column-major N x N) via utils::hermitian: value computed for i<=j and mirrored
+ * (scf/src/lib.rs:118-128; BasisFunction impls basis/src/contracted_gaussian.rs:209-262).
+ * Negative angular components (kinetic term2) give 0 through hermite_expansion's t>i+j test
+ * only when multiplied by the zero l(l-1) factor; the reference relies on the same. */
+void oracle_one_electron(const oracle_basis *bs, int n_nuclei, const double *nuc_pos, const double *nuc_charge,
+                         int flags, double *S, double *T, double *V) {
+    const int n = bs->n_basis;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int j = 0; j < n; ++j) {
+        for (int i = 0; i <= j; ++i) {
+            const double *ap = bs->center + 3 * i, *bp = bs->center + 3 * j;
+            double diff[3] = {bp[0] - ap[0], bp[1] - ap[1], bp[2] - ap[2]};
+            int la[3], lb[3];
+            for (int k = 0; k < 3; ++k) {
+                la[k] = bs->angular[3 * i + k];
+                lb[k] = bs->angular[3 * j + k];
+            }
+            double s = 0.0, t = 0.0;
+            for (int a = bs->prim_offset[i]; a < bs->prim_offset[i + 1]; ++a)
+                for (int b = bs->prim_offset[j]; b < bs->prim_offset[j + 1]; ++b) {
+                    double cc = bs->coefficient[a] * bs->coefficient[b];
+                    s += cc * prim_overlap(la, bs->exponent[a], lb, bs->exponent[b], diff);
+                    t += cc * prim_kinetic(la, bs->exponent[a], lb, bs->exponent[b], diff);
+                }
+            double v = 0.0;
+            for (int c = 0; c < n_nuclei; ++c)
+                for (int a = bs->prim_offset[i]; a < bs->prim_offset[i + 1]; ++a)
+                    for (int b = bs->prim_offset[j]; b < bs->prim_offset[j + 1]; ++b) {
+                        double pc[3];
+                        product_center(bs->exponent[a], ap, bs->exponent[b], bp, pc);
+                        v += bs->coefficient[a] * bs->coefficient[b] *
+                             prim_nuclear(la, bs->exponent[a], lb, bs->exponent[b], diff, pc, nuc_pos + 3 * c,
+                                          nuc_charge[c], flags);
+                    }
+            S[i + (size_t)j * n] = S[j + (size_t)i * n] = s;
+            T[i + (size_t)j * n] = T[j + (size_t)i * n] = t;
+            V[i + (size_t)j * n] = V[j + (size_t)i * n] = v;
+        }
+    }
+}
