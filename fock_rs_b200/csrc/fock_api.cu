@@ -1,0 +1,599 @@
+// fock_api.cu -- implementation of the C ABI in include/fock_b200.h.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <new>
+
+#include "class_launch.h"
+#include "context.h"
+#include "eri_class.cuh"
+#include "tensor_kernels.cuh"
+
+using namespace fock;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+const double kBoysLut[200] = {
+#include "boys_lut.inc"
+};
+
+// Accurate-mode grid F_n(k*DT): series  F_n(T) = exp(-T) sum_k (2T)^k / ((2n+1)(2n+3)...(2n+2k+1)).
+void make_boys_table(std::vector<double> &tab) {
+    tab.resize((size_t)BOYS_TAB_POINTS * BOYS_TAB_ORDERS);
+    for (int k = 0; k < BOYS_TAB_POINTS; ++k) {
+        const long double t = (long double)k * (long double)BOYS_TAB_DT;
+        for (int n = 0; n < BOYS_TAB_ORDERS; ++n) {
+            long double term = 1.0L / (2 * n + 1), sum = term;
+            for (int j = 1; j < 600; ++j) {
+                term *= 2.0L * t / (2 * n + 2 * j + 1);
+                sum += term;
+                if (term < 1e-22L * sum) break;
+            }
+            tab[(size_t)k * BOYS_TAB_ORDERS + n] = (double)(expl(-t) * sum);
+        }
+    }
+}
+
+struct ClassState {
+    ClassEngine engine;
+    ClassStats stats;
+    unsigned char *d_bf_class_ok = nullptr;
+    unsigned long long *d_counter = nullptr;
+};
+
+ClassState *cls(fock_ctx *ctx);
+
+}  // namespace
+
+// the class engine lives beside the context (kept out of context.h to keep that header light)
+struct fock_ctx_ext : fock_ctx {
+    ClassState cs;
+};
+namespace {
+ClassState *cls(fock_ctx *ctx) { return &static_cast<fock_ctx_ext *>(ctx)->cs; }
+
+double screen_threshold(const fock_opts &o) { return o.screen == FOCK_SCREEN_SCHWARZ ? o.tau : 1e-6; }
+
+int ensure_g_buffers(fock_ctx *ctx) {
+    const size_t nn = (size_t)ctx->N * ctx->N;
+    if (!ctx->d_dvec) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_dvec, ctx->npair * sizeof(double)));
+    if (!ctx->d_yvec) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_yvec, ctx->npair * sizeof(double)));
+    if (!ctx->d_D) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_D, nn * sizeof(double)));
+    if (!ctx->d_G) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_G, nn * sizeof(double)));
+    if (!ctx->h_pinned) FOCK_CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_pinned, 2 * nn * sizeof(double)));
+    return FOCK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fock_abi_version(void) { return FOCK_B200_ABI_VERSION; }
+
+void fock_default_opts(fock_opts *o) {
+    if (!o) return;
+    std::memset(o, 0, sizeof(*o));
+    o->mode = FOCK_MODE_FAITHFUL;
+    o->screen = FOCK_SCREEN_REFERENCE;
+    o->tau = 1e-6;
+    o->storage = FOCK_STORAGE_INCORE;
+    o->device = -1;
+    o->rank = 0;
+    o->world = 1;
+    o->keep_eri = 1;
+    o->kernel = 0;
+}
+
+size_t fock_packed_len(int32_t n) {
+    const size_t p = (size_t)n * ((size_t)n + 1) / 2;
+    return p * (p + 1) / 2;
+}
+
+const char *fock_last_error(fock_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int fock_create(const fock_basis *b, const fock_opts *opts_in, fock_ctx **out) {
+    g_create_error.clear();
+    if (!b || !out) {
+        g_create_error = "null argument";
+        return FOCK_ERR_BAD_ARG;
+    }
+    *out = nullptr;
+    fock_opts o;
+    if (opts_in) o = *opts_in; else fock_default_opts(&o);
+    if (b->n_basis <= 0 || !b->center || !b->angular || !b->prim_offset || !b->exponent || !b->coefficient) {
+        g_create_error = "empty or incomplete basis";
+        return FOCK_ERR_BAD_ARG;
+    }
+    if (o.world < 1 || o.rank < 0 || o.rank >= o.world || (o.mode & ~3) || o.screen < 0 || o.screen > 2 ||
+        o.storage < 0 || o.storage > 1) {
+        g_create_error = "bad options";
+        return FOCK_ERR_BAD_ARG;
+    }
+    const int n = b->n_basis;
+    for (int i = 0; i < n; ++i) {
+        const int l = b->angular[3 * i] + b->angular[3 * i + 1] + b->angular[3 * i + 2];
+        if (b->angular[3 * i] < 0 || b->angular[3 * i + 1] < 0 || b->angular[3 * i + 2] < 0 ||
+            b->prim_offset[i + 1] <= b->prim_offset[i]) {
+            g_create_error = "malformed basis function";
+            return FOCK_ERR_BAD_ARG;
+        }
+        if (l > 4) {
+            g_create_error = "angular momentum above g is not supported";
+            return FOCK_ERR_UNSUPPORTED;
+        }
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        g_create_error = "no CUDA device (this library has no CPU fallback)";
+        return FOCK_ERR_CUDA;
+    }
+    fock_ctx_ext *ctx = new (std::nothrow) fock_ctx_ext();
+    if (!ctx) return FOCK_ERR_OOM;
+    std::unique_ptr<fock_ctx_ext, void (*)(fock_ctx_ext *)> guard(ctx, [](fock_ctx_ext *c) { fock_destroy(c); });
+    auto fail = [&](int code) {
+        g_create_error = ctx->err;
+        return code;
+    };
+    ctx->opts = o;
+    if (o.device >= 0) {
+        if (cudaSetDevice(o.device) != cudaSuccess) {
+            ctx->err = "cudaSetDevice failed";
+            return fail(FOCK_ERR_CUDA);
+        }
+    }
+    cudaGetDevice(&ctx->device);
+    ctx->N = n;
+    ctx->npair = (size_t)n * (n + 1) / 2;
+    ctx->nelem = ctx->npair * (ctx->npair + 1) / 2;
+    ctx->nprim = b->prim_offset[n];
+    ctx->h_center.assign(b->center, b->center + 3 * n);
+    ctx->h_angular.assign(b->angular, b->angular + 3 * n);
+    ctx->h_primoff.assign(b->prim_offset, b->prim_offset + n + 1);
+    ctx->h_exp.assign(b->exponent, b->exponent + ctx->nprim);
+    ctx->h_coef.assign(b->coefficient, b->coefficient + ctx->nprim);
+
+    auto body = [&]() -> int {
+        FOCK_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        ctx->stream = ctx->own_stream;
+        for (int i = 0; i < EV_COUNT; ++i) FOCK_CUDA_TRY(ctx, cudaEventCreate(&ctx->ev[i]));
+        FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_center, 3 * n * sizeof(double)));
+        FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_angular, 3 * n * sizeof(int)));
+        FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_primoff, (n + 1) * sizeof(int)));
+        FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_exp, ctx->nprim * sizeof(double)));
+        FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_coef, ctx->nprim * sizeof(double)));
+        FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_boys_lut, 200 * sizeof(double)));
+        FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_boys_tab, (size_t)BOYS_TAB_POINTS * BOYS_TAB_ORDERS * sizeof(double)));
+        FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_diag, ctx->npair * sizeof(double)));
+        std::vector<double> tab;
+        make_boys_table(tab);
+        cudaStream_t st = ctx->stream;
+        FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_center, ctx->h_center.data(), 3 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+        FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_angular, ctx->h_angular.data(), 3 * n * sizeof(int), cudaMemcpyHostToDevice, st));
+        FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_primoff, ctx->h_primoff.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_exp, ctx->h_exp.data(), ctx->nprim * sizeof(double), cudaMemcpyHostToDevice, st));
+        FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_coef, ctx->h_coef.data(), ctx->nprim * sizeof(double), cudaMemcpyHostToDevice, st));
+        FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_boys_lut, kBoysLut, sizeof(kBoysLut), cudaMemcpyHostToDevice, st));
+        FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_boys_tab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+        FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+
+        // shells, pairs, class tables
+        std::string err;
+        if (!build_shells(n, b->center, b->angular, b->prim_offset, b->exponent, b->coefficient, ctx->shells, err)) {
+            ctx->err = err;
+            return FOCK_ERR_BAD_ARG;
+        }
+        if (o.kernel == 1) {
+            for (Shell &s : ctx->shells.shells) s.class_ok = false;
+            ctx->shells.all_class_ok = false;
+            ctx->shells.n_class_shells = 0;
+        }
+        build_pairs(ctx->shells);
+        ClassState *cs = &ctx->cs;
+        cs->engine.sd = &ctx->shells;
+        cs->engine.dev = &ctx->pairs;
+        cs->engine.boys = ctx->boys();
+        cs->engine.stream = ctx->stream;
+        cs->engine.mode = o.mode;
+        if (!ctx->shells.pairs.empty() && cs->engine.upload_tables(err)) {
+            ctx->err = err;
+            return FOCK_ERR_CUDA;
+        }
+        std::vector<unsigned char> ok(n);
+        for (int i = 0; i < n; ++i) ok[i] = ctx->shells.shells[ctx->shells.bf_shell[i]].class_ok ? 1 : 0;
+        FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&cs->d_bf_class_ok, n));
+        FOCK_CUDA_TRY(ctx, cudaMemcpy(cs->d_bf_class_ok, ok.data(), n, cudaMemcpyHostToDevice));
+        FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&cs->d_counter, sizeof(unsigned long long)));
+        ctx->digest_begin = 0;
+        ctx->digest_end = ctx->nelem;
+        ctx->stats[0] = n;
+        ctx->stats[1] = (int64_t)ctx->shells.shells.size();
+        ctx->stats[2] = (int64_t)(ctx->shells.shells.size() * (ctx->shells.shells.size() + 1) / 2);
+        {
+            const int64_t sp = ctx->stats[2];
+            ctx->stats[3] = sp * (sp + 1) / 2;
+        }
+        return FOCK_OK;
+    };
+    const int status = body();
+    if (status != FOCK_OK) return fail(status);
+    *out = guard.release();
+    return FOCK_OK;
+}
+
+void fock_destroy(fock_ctx *c) {
+    if (!c) return;
+    fock_ctx_ext *ctx = static_cast<fock_ctx_ext *>(c);
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    void *ptrs[] = {ctx->d_center, ctx->d_angular, ctx->d_primoff, ctx->d_exp,  ctx->d_coef, ctx->d_boys_lut,
+                    ctx->d_boys_tab, ctx->d_diag,   ctx->d_V,       ctx->d_P,    ctx->d_dvec, ctx->d_yvec,
+                    ctx->d_D,      ctx->d_G,       ctx->pairs.d_bra, ctx->pairs.d_ket, ctx->pairs.d_meta,
+                    ctx->pairs.d_shell_bf, ctx->pairs.d_maxdiag, ctx->cs.d_bf_class_ok, ctx->cs.d_counter};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int i = 0; i < EV_COUNT; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int fock_set_stream(fock_ctx *ctx, void *s) {
+    if (!ctx) return FOCK_ERR_BAD_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    cls(ctx)->engine.stream = ctx->stream;
+    return FOCK_OK;
+}
+
+// Diagonal pass shared by both storage modes: fills d_diag and orders the class sublists.
+static int diagonal_pass(fock_ctx *ctx, int *launches) {
+    ClassState *cs = cls(ctx);
+    cudaStream_t st = ctx->stream;
+    const int T = 128;
+    std::string err;
+    FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_diag, 0, ctx->npair * sizeof(double), st));
+    if (!ctx->shells.pairs.empty()) {
+        const int l = cs->engine.run_diagonal(ctx->d_diag, err);
+        if (l < 0) {
+            ctx->err = err;
+            return FOCK_ERR_CUDA;
+        }
+        *launches += l;
+    }
+    if (!ctx->shells.all_class_ok) {
+        generic_diag_kernel<<<(unsigned)((ctx->npair + T - 1) / T), T, 0, st>>>(ctx->basis_dev(), ctx->boys(), ctx->opts.mode,
+                                                                              cs->d_bf_class_ok, 1, ctx->npair, ctx->d_diag);
+        *launches += 1;
+    }
+    FOCK_CUDA_TRY(ctx, cudaGetLastError());
+    if (!ctx->shells.pairs.empty()) {
+        std::vector<double> h_diag(ctx->npair);
+        FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(h_diag.data(), ctx->d_diag, ctx->npair * sizeof(double), cudaMemcpyDeviceToHost, st));
+        FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (cs->engine.sort_by_diagonal(h_diag, err)) {
+            ctx->err = err;
+            return FOCK_ERR_CUDA;
+        }
+    }
+    return FOCK_OK;
+}
+
+int fock_eri_build(fock_ctx *ctx) {
+    if (!ctx) return FOCK_ERR_BAD_ARG;
+    FOCK_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    // reference: boys() asserts n <= 10 (boys/src/lib.rs:59-62); total L of a quartet is the max order
+    {
+        int lmax = 0;
+        for (int i = 0; i < ctx->N; ++i)
+            lmax = std::max(lmax, ctx->h_angular[3 * i] + ctx->h_angular[3 * i + 1] + ctx->h_angular[3 * i + 2]);
+        if (4 * lmax > 10) {
+            ctx->err = "Boys-Function order is higher than max tabulated order 10";
+            return FOCK_ERR_BOYS_ORDER;
+        }
+    }
+    ClassState *cs = cls(ctx);
+    cudaStream_t st = ctx->stream;
+    int launches = 0;
+    const int T = 128;
+    FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_A], st));
+    FOCK_TRY(diagonal_pass(ctx, &launches));
+    FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_B], st));
+    ctx->stats[4] = ctx->stats[5] = 0;
+    ctx->stats[8] = 0;
+    if (ctx->opts.storage == FOCK_STORAGE_INCORE) {
+        if (!ctx->d_V) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_V, ctx->nelem * sizeof(double)));
+        FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_V, 0, ctx->nelem * sizeof(double), st));
+        FOCK_CUDA_TRY(ctx, cudaMemsetAsync(cs->d_counter, 0, sizeof(unsigned long long), st));
+        const double thr = screen_threshold(ctx->opts);
+        if (!ctx->shells.pairs.empty()) {
+            StoreSink sink{ctx->d_V, ctx->d_diag, thr, ctx->opts.screen};
+            std::string err;
+            const int l = cs->engine.run_build(sink, ctx->opts.screen, thr, ctx->opts.rank, ctx->opts.world, cs->stats, err);
+            if (l < 0) {
+                ctx->err = err;
+                return FOCK_ERR_CUDA;
+            }
+            launches += l;
+            ctx->stats[4] = cs->stats.shell_quartets;
+            ctx->stats[5] = cs->stats.prim_quartets;
+            ctx->stats[8] = (int64_t)cs->stats.model_flops;
+        }
+        if (!ctx->shells.all_class_ok) {
+            const size_t mine = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
+            generic_tensor_kernel<<<(unsigned)((mine + T - 1) / T), T, 0, st>>>(
+                ctx->basis_dev(), ctx->boys(), ctx->opts.mode, cs->d_bf_class_ok, 1, ctx->opts.screen, thr, ctx->d_diag,
+                ctx->nelem, ctx->opts.rank, ctx->opts.world, ctx->d_V, cs->d_counter);
+            launches += 1;
+        }
+        FOCK_CUDA_TRY(ctx, cudaGetLastError());
+        FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_C], st));
+        const size_t chunk = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
+        const size_t padded = chunk * ctx->opts.world;  // equal chunks for the reduce-scatter
+        if (!ctx->d_P) {
+            FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_P, padded * sizeof(double)));
+            if (padded > ctx->nelem)
+                FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_P + ctx->nelem, 0, (padded - ctx->nelem) * sizeof(double), st));
+        }
+        supermatrix_kernel<<<(unsigned)((ctx->nelem + 255) / 256), 256, 0, st>>>(ctx->d_V, ctx->d_P, ctx->nelem);
+        launches += 1;
+        FOCK_CUDA_TRY(ctx, cudaGetLastError());
+        FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_D], st));
+        unsigned long long generic_eval = 0;
+        FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(&generic_eval, cs->d_counter, sizeof(generic_eval), cudaMemcpyDeviceToHost, st));
+        FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        ctx->stats[9] = (int64_t)generic_eval;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[EV_A], ctx->ev[EV_B]);
+        ctx->timings[0] = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[EV_B], ctx->ev[EV_C]);
+        ctx->timings[1] = ms;
+        cudaEventElapsedTime(&ms, ctx->ev[EV_C], ctx->ev[EV_D]);
+        ctx->timings[2] = ms;
+        if (!ctx->opts.keep_eri) {
+            cudaFree(ctx->d_V);
+            ctx->d_V = nullptr;
+        }
+    } else {
+        FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[EV_A], ctx->ev[EV_B]);
+        ctx->timings[0] = ms;
+        ctx->timings[1] = ctx->timings[2] = 0;
+    }
+    ctx->stats[6] = launches;
+    ctx->built = true;
+    return FOCK_OK;
+}
+
+int fock_eri_get(fock_ctx *ctx, int32_t i, int32_t j, int32_t k, int32_t l, double *value) {
+    if (!ctx || !value) return FOCK_ERR_BAD_ARG;
+    const int n = ctx->N;
+    if (i < 0 || j < 0 || k < 0 || l < 0 || i >= n || j >= n || k >= n || l >= n) {
+        ctx->err = "index out of range";
+        return FOCK_ERR_BAD_ARG;
+    }
+    if (!ctx->built || !ctx->d_V) {
+        ctx->err = "fock_eri_get needs fock_eri_build with in-core storage and keep_eri";
+        return FOCK_ERR_STATE;
+    }
+    FOCK_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(value, ctx->d_V + packed_index(i, j, k, l), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return FOCK_OK;
+}
+
+int fock_eri_export_packed(fock_ctx *ctx, double *host, size_t n) {
+    if (!ctx || !host) return FOCK_ERR_BAD_ARG;
+    if (n != ctx->nelem) {
+        ctx->err = "export size must be fock_packed_len(N)";
+        return FOCK_ERR_BAD_ARG;
+    }
+    if (!ctx->built || !ctx->d_V) {
+        ctx->err = "fock_eri_export_packed needs fock_eri_build with in-core storage and keep_eri";
+        return FOCK_ERR_STATE;
+    }
+    FOCK_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(host, ctx->d_V, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return FOCK_OK;
+}
+
+int fock_eri_batch(fock_ctx *ctx, const int32_t *quartets, size_t n, double *values) {
+    if (!ctx || (!quartets && n) || (!values && n)) return FOCK_ERR_BAD_ARG;
+    if (n == 0) return FOCK_OK;
+    for (size_t i = 0; i < 4 * n; ++i)
+        if (quartets[i] < 0 || quartets[i] >= ctx->N) {
+            ctx->err = "quartet index out of range";
+            return FOCK_ERR_BAD_ARG;
+        }
+    for (size_t i = 0; i < n; ++i) {
+        int L = 0;
+        for (int k = 0; k < 4; ++k) {
+            const int f = quartets[4 * i + k];
+            L += ctx->h_angular[3 * f] + ctx->h_angular[3 * f + 1] + ctx->h_angular[3 * f + 2];
+        }
+        if (L > 10) {
+            ctx->err = "Boys-Function order is higher than max tabulated order 10";
+            return FOCK_ERR_BOYS_ORDER;
+        }
+    }
+    FOCK_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int *d_q = nullptr;
+    double *d_o = nullptr;
+    FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&d_q, 4 * n * sizeof(int)));
+    cudaError_t e = cudaMalloc((void **)&d_o, n * sizeof(double));
+    if (e != cudaSuccess) {
+        cudaFree(d_q);
+        ctx->err = cudaGetErrorString(e);
+        return FOCK_ERR_OOM;
+    }
+    cudaStream_t st = ctx->stream;
+    cudaMemcpyAsync(d_q, quartets, 4 * n * sizeof(int), cudaMemcpyHostToDevice, st);
+    generic_batch_kernel<<<(unsigned)((n + 63) / 64), 64, 0, st>>>(ctx->basis_dev(), ctx->boys(), ctx->opts.mode, d_q, n, d_o);
+    cudaMemcpyAsync(values, d_o, n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    cudaFree(d_q);
+    cudaFree(d_o);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("fock_eri_batch: ") + cudaGetErrorString(e);
+        return FOCK_ERR_CUDA;
+    }
+    return FOCK_OK;
+}
+
+int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev) {
+    if (!ctx || !D_dev || !G_dev) return FOCK_ERR_BAD_ARG;
+    if (!ctx->built) {
+        ctx->err = "fock_build_g before fock_eri_build";
+        return FOCK_ERR_STATE;
+    }
+    FOCK_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FOCK_TRY(ensure_g_buffers(ctx));
+    cudaStream_t st = ctx->stream;
+    int launches = 0;
+    FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_E], st));
+    if (ctx->opts.storage == FOCK_STORAGE_INCORE) {
+        if (!ctx->d_P) {
+            ctx->err = "supermatrix missing";
+            return FOCK_ERR_STATE;
+        }
+        pack_density_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(D_dev, ctx->N, ctx->d_dvec, ctx->d_yvec, ctx->npair);
+        // rows that intersect [digest_begin, digest_end)
+        size_t r_first = 0, r_last = ctx->npair - 1, c;
+        if (ctx->digest_end > ctx->digest_begin) {
+            untri(ctx->digest_begin, r_first, c);
+            untri(ctx->digest_end - 1, r_last, c);
+            r_first = r_first / kSymvRB * kSymvRB;
+            const size_t nstrips = (r_last - r_first) / kSymvRB + 1;
+            const size_t nchunks = r_last / kSymvCB + 1;
+            dim3 grid((unsigned)nchunks, (unsigned)nstrips);
+            if (nstrips > 65535) {
+                // split the strip range over several launches (grid.y limit)
+                for (size_t s0 = 0; s0 < nstrips; s0 += 65535) {
+                    const size_t ns = std::min<size_t>(65535, nstrips - s0);
+                    dim3 g((unsigned)nchunks, (unsigned)ns);
+                    symv_packed_kernel<<<g, kSymvThreads, 0, st>>>(ctx->d_P, ctx->d_dvec, ctx->d_yvec, ctx->npair, ctx->digest_begin,
+                                                                  ctx->digest_end, r_first + s0 * kSymvRB);
+                    ++launches;
+                }
+            } else {
+                symv_packed_kernel<<<grid, kSymvThreads, 0, st>>>(ctx->d_P, ctx->d_dvec, ctx->d_yvec, ctx->npair, ctx->digest_begin,
+                                                                 ctx->digest_end, r_first);
+                ++launches;
+            }
+        }
+        unpack_result_kernel<<<(unsigned)(((size_t)ctx->N * ctx->N + 255) / 256), 256, 0, st>>>(ctx->d_yvec, ctx->N, G_dev);
+        launches += 2;
+    } else {
+        ctx->err = "integral-direct G build is not available in this build";
+        return FOCK_ERR_UNSUPPORTED;
+    }
+    FOCK_CUDA_TRY(ctx, cudaGetLastError());
+    FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_F], st));
+    ctx->stats[7] = launches;
+    return FOCK_OK;
+}
+
+int fock_build_g(fock_ctx *ctx, const double *D, double *G) {
+    if (!ctx || !D || !G) return FOCK_ERR_BAD_ARG;
+    if (!ctx->built) {
+        ctx->err = "fock_build_g before fock_eri_build";
+        return FOCK_ERR_STATE;
+    }
+    FOCK_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FOCK_TRY(ensure_g_buffers(ctx));
+    const size_t nn = (size_t)ctx->N * ctx->N;
+    cudaStream_t st = ctx->stream;
+    std::memcpy(ctx->h_pinned, D, nn * sizeof(double));
+    FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_C], st));
+    FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_D, ctx->h_pinned, nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    FOCK_TRY(fock_build_g_device(ctx, ctx->d_D, ctx->d_G));
+    FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned + nn, ctx->d_G, nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_D], st));
+    FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    std::memcpy(G, ctx->h_pinned + nn, nn * sizeof(double));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[EV_E], ctx->ev[EV_F]);
+    ctx->timings[3] = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[EV_C], ctx->ev[EV_D]);
+    ctx->timings[4] = ms;
+    return FOCK_OK;
+}
+
+int fock_one_electron(fock_ctx *ctx, int32_t n_nuc, const double *pos, const double *chg, double *S, double *T, double *V) {
+    if (!ctx || n_nuc < 0 || (n_nuc && (!pos || !chg)) || !S || !T || !V) return FOCK_ERR_BAD_ARG;
+    FOCK_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int n = ctx->N;
+    const size_t nn = (size_t)n * n;
+    {
+        int lmax = 0;
+        for (int i = 0; i < n; ++i) lmax = std::max(lmax, ctx->h_angular[3 * i] + ctx->h_angular[3 * i + 1] + ctx->h_angular[3 * i + 2]);
+        if (2 * lmax > 10) {
+            ctx->err = "Boys-Function order is higher than max tabulated order 10";
+            return FOCK_ERR_BOYS_ORDER;
+        }
+    }
+    double *d_buf = nullptr;
+    FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&d_buf, (3 * nn + 4 * (size_t)std::max(n_nuc, 1)) * sizeof(double)));
+    double *dS = d_buf, *dT = d_buf + nn, *dV = d_buf + 2 * nn, *dpos = d_buf + 3 * nn, *dchg = dpos + 3 * (size_t)std::max(n_nuc, 1);
+    cudaStream_t st = ctx->stream;
+    if (n_nuc) {
+        cudaMemcpyAsync(dpos, pos, 3 * n_nuc * sizeof(double), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(dchg, chg, n_nuc * sizeof(double), cudaMemcpyHostToDevice, st);
+    }
+    const size_t np = ctx->npair;
+    one_electron_kernel<<<(unsigned)((np + 63) / 64), 64, 0, st>>>(ctx->basis_dev(), ctx->boys(), ctx->opts.mode, n_nuc, dpos, dchg, dS, dT, dV);
+    cudaMemcpyAsync(S, dS, nn * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(T, dT, nn * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(V, dV, nn * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d_buf);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("fock_one_electron: ") + cudaGetErrorString(e);
+        return FOCK_ERR_CUDA;
+    }
+    return FOCK_OK;
+}
+
+int fock_supermatrix_device(fock_ctx *ctx, void **dev_ptr, size_t *n_elements) {
+    if (!ctx || !dev_ptr || !n_elements) return FOCK_ERR_BAD_ARG;
+    if (!ctx->d_P) {
+        ctx->err = "no supermatrix (in-core fock_eri_build first)";
+        return FOCK_ERR_STATE;
+    }
+    *dev_ptr = ctx->d_P;
+    const size_t chunk = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
+    *n_elements = chunk * ctx->opts.world;  // padded length (>= fock_packed_len(N))
+    return FOCK_OK;
+}
+
+int fock_set_digest_range(fock_ctx *ctx, size_t begin, size_t end) {
+    if (!ctx || begin > end || end > ctx->nelem) return FOCK_ERR_BAD_ARG;
+    ctx->digest_begin = begin;
+    ctx->digest_end = end;
+    return FOCK_OK;
+}
+
+int fock_timings(fock_ctx *ctx, double *ms, int32_t n) {
+    if (!ctx || !ms || n < 0) return FOCK_ERR_BAD_ARG;
+    // the device-pointer G build leaves its events unread until asked
+    if (ctx->built && ctx->ev[EV_F] && cudaEventQuery(ctx->ev[EV_F]) == cudaSuccess) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, ctx->ev[EV_E], ctx->ev[EV_F]) == cudaSuccess) ctx->timings[3] = t;
+    }
+    cudaGetLastError();
+    for (int i = 0; i < n && i < 8; ++i) ms[i] = ctx->timings[i];
+    return FOCK_OK;
+}
+
+int fock_stats(fock_ctx *ctx, int64_t *out, int32_t n) {
+    if (!ctx || !out || n < 0) return FOCK_ERR_BAD_ARG;
+    for (int i = 0; i < n && i < 16; ++i) out[i] = ctx->stats[i];
+    return FOCK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,225 @@
+"""Host-side mirror of the reference's two-electron interface, backed by the CUDA library.
+
+  ElectronTensor.from_basis(basis)  <->  basis/src/electron_tensor.rs:81   (+ `tensor[(i,j,k,l)]`, :179)
+  FockBuilder.build_g(D)            <->  scf/src/lib.rs:177-185            (the per-iteration G loop)
+  electron_repulsion_int(a,b,c,d)   <->  basis/src/lib.rs:41
+  FockEngine                        <->  the three call sites of scf/src/lib.rs:118-185 as one object
+                                         (plugs into fock_rs_b200.scf.try_scf)
+
+Everything computes on the GPU through the C ABI (include/fock_b200.h); nothing here has a CPU path.
+With torch.distributed initialised (one process per GPU) the quartet tiles are sharded over ranks and
+partial G matrices are summed with one all-reduce per iteration.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import FockError
+from .basis_set import ContractedGaussian, FlatBasis, flatten
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _as_flat(basis) -> FlatBasis:
+    if isinstance(basis, FlatBasis):
+        return basis
+    return flatten(list(basis))
+
+
+class FockBuilder:
+    """Owns one `fock_ctx`.  Options mirror `fock_opts` (include/fock_b200.h)."""
+
+    def __init__(self, basis, mode=_lib.MODE_FAITHFUL, screen=_lib.SCREEN_REFERENCE, tau=1e-6, storage=_lib.STORAGE_INCORE,
+                 device=-1, rank=0, world=1, keep_eri=True, kernel=0):
+        self._L = _lib.load()
+        self._ctx = C.c_void_p()
+        flat = _as_flat(basis)
+        self.flat = flat
+        self.n = flat.n_basis
+        # keep the arrays alive for the duration of fock_create
+        center = np.ascontiguousarray(flat.center, dtype=np.float64)
+        angular = np.ascontiguousarray(flat.angular, dtype=np.int32)
+        off = np.ascontiguousarray(flat.prim_offset, dtype=np.int32)
+        exps = np.ascontiguousarray(flat.exponent, dtype=np.float64)
+        coefs = np.ascontiguousarray(flat.coefficient, dtype=np.float64)
+        cb = _lib.CBasis(self.n, _dp(center), angular.ctypes.data_as(C.POINTER(C.c_int32)), off.ctypes.data_as(C.POINTER(C.c_int32)), _dp(exps), _dp(coefs))
+        opts = _lib.COpts()
+        self._L.fock_default_opts(C.byref(opts))
+        opts.mode, opts.screen, opts.tau, opts.storage = int(mode), int(screen), float(tau), int(storage)
+        opts.device, opts.rank, opts.world, opts.keep_eri, opts.kernel = int(device), int(rank), int(world), int(bool(keep_eri)), int(kernel)
+        self.opts = opts
+        st = self._L.fock_create(C.byref(cb), C.byref(opts), C.byref(self._ctx))
+        if st != _lib.OK:
+            msg = self._L.fock_last_error(None)
+            self._ctx = C.c_void_p()
+            raise FockError(st, msg.decode() if msg else "fock_create failed")
+
+    # -- plumbing
+    def _check(self, st):
+        if st != _lib.OK:
+            msg = self._L.fock_last_error(self._ctx)
+            raise FockError(st, msg.decode() if msg else "")
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._L.fock_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- the path
+    def eri_build(self):
+        """ElectronTensor::from_basis (+ the electron_terms precompute)."""
+        self._check(self._L.fock_eri_build(self._ctx))
+        return self
+
+    def eri_get(self, i, j, k, l) -> float:
+        v = C.c_double()
+        self._check(self._L.fock_eri_get(self._ctx, i, j, k, l, C.byref(v)))
+        return v.value
+
+    def eri_export_packed(self) -> np.ndarray:
+        out = np.empty(self._L.fock_packed_len(self.n), dtype=np.float64)
+        self._check(self._L.fock_eri_export_packed(self._ctx, _dp(out), out.size))
+        return out
+
+    def eri_batch(self, quartets) -> np.ndarray:
+        q = np.ascontiguousarray(quartets, dtype=np.int32).reshape(-1, 4)
+        out = np.empty(q.shape[0], dtype=np.float64)
+        self._check(self._L.fock_eri_batch(self._ctx, q.ctypes.data_as(C.POINTER(C.c_int32)), q.shape[0], _dp(out)))
+        return out
+
+    def build_g(self, D) -> np.ndarray:
+        """G = J - K/2 for a symmetric density (host buffers, column-major like DMatrix)."""
+        Dc = np.asfortranarray(D, dtype=np.float64)
+        if Dc.shape != (self.n, self.n):
+            raise ValueError("density must be N x N")
+        G = np.empty((self.n, self.n), dtype=np.float64, order="F")
+        self._check(self._L.fock_build_g(self._ctx, _dp(Dc), _dp(G)))
+        return G
+
+    def build_g_device(self, d_ptr: int, g_ptr: int):
+        """Device-resident D and G (raw device pointers, N*N doubles each, column-major)."""
+        self._check(self._L.fock_build_g_device(self._ctx, C.c_void_p(d_ptr), C.c_void_p(g_ptr)))
+
+    def one_electron(self, nuc_pos, nuc_charge):
+        pos = np.ascontiguousarray(nuc_pos, dtype=np.float64).reshape(-1, 3)
+        chg = np.ascontiguousarray(nuc_charge, dtype=np.float64)
+        n = self.n
+        S, T, V = (np.empty((n, n), dtype=np.float64, order="F") for _ in range(3))
+        self._check(self._L.fock_one_electron(self._ctx, pos.shape[0], _dp(pos), _dp(chg), _dp(S), _dp(T), _dp(V)))
+        return S, T, V
+
+    def set_stream(self, stream_ptr: Optional[int]):
+        self._check(self._L.fock_set_stream(self._ctx, C.c_void_p(stream_ptr or 0)))
+
+    def supermatrix_device(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self._L.fock_supermatrix_device(self._ctx, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def set_digest_range(self, begin: int, end: int):
+        self._check(self._L.fock_set_digest_range(self._ctx, begin, end))
+
+    def timings(self) -> dict:
+        ms = (C.c_double * 8)()
+        self._check(self._L.fock_timings(self._ctx, ms, 8))
+        return {"diag_ms": ms[0], "eri_ms": ms[1], "supermatrix_ms": ms[2], "g_device_ms": ms[3], "g_e2e_ms": ms[4]}
+
+    def stats(self) -> dict:
+        s = (C.c_int64 * 16)()
+        self._check(self._L.fock_stats(self._ctx, s, 16))
+        return {
+            "n_basis": s[0], "shells": s[1], "shell_pairs": s[2], "shell_quartets_unique": s[3],
+            "shell_quartets_evaluated": s[4], "prim_quartets_evaluated": s[5], "launches_build": s[6],
+            "launches_g": s[7], "model_flops": s[8], "generic_integrals_evaluated": s[9],
+        }
+
+
+class ElectronTensor:
+    """`ElectronTensor::from_basis(&basis)` + `tensor[(i,j,k,l)]` (basis/src/electron_tensor.rs:81,179)."""
+
+    def __init__(self, builder: FockBuilder):
+        self.builder = builder
+        self.size = builder.n
+
+    @classmethod
+    def from_basis(cls, basis: Sequence[ContractedGaussian], **opts) -> "ElectronTensor":
+        return cls(FockBuilder(basis, **opts).eri_build())
+
+    def __getitem__(self, idx) -> float:
+        i, j, k, l = idx
+        return self.builder.eri_get(int(i), int(j), int(k), int(l))
+
+    def packed(self) -> np.ndarray:
+        return self.builder.eri_export_packed()
+
+
+def electron_repulsion_int(a: ContractedGaussian, b: ContractedGaussian, c: ContractedGaussian, d: ContractedGaussian, mode=_lib.MODE_FAITHFUL) -> float:
+    """`BasisFunction::electron_repulsion_int(a, b, c, d)` (basis/src/lib.rs:41) on the GPU."""
+    with FockBuilder([a, b, c, d], mode=mode) as fb:
+        return float(fb.eri_batch([[0, 1, 2, 3]])[0])
+
+
+class FockEngine:
+    """The engine `try_scf` drives (see fock_rs_b200.scf).  Rank/world come from torch.distributed
+    when it is initialised; partial G matrices are all-reduced over NCCL."""
+
+    def __init__(self, mode=_lib.MODE_FAITHFUL, screen=_lib.SCREEN_REFERENCE, tau=1e-6, storage=_lib.STORAGE_INCORE, device=-1, distributed=None):
+        self.kw = dict(mode=mode, screen=screen, tau=tau, storage=storage, device=device)
+        self.builder: Optional[FockBuilder] = None
+        self.rank, self.world = 0, 1
+        if distributed is None:
+            try:
+                import torch.distributed as dist
+
+                distributed = dist.is_available() and dist.is_initialized()
+            except Exception:
+                distributed = False
+        self.distributed = bool(distributed)
+        if self.distributed:
+            import torch.distributed as dist
+
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def _ensure(self, flat):
+        if self.builder is None or self.builder.flat is not flat:
+            if self.builder is not None:
+                self.builder.close()
+            self.builder = FockBuilder(flat, rank=self.rank, world=self.world, **self.kw)
+        return self.builder
+
+    def one_electron(self, flat, nuc_pos, nuc_chg):
+        return self._ensure(flat).one_electron(nuc_pos, nuc_chg)
+
+    def from_basis(self, flat):
+        b = self._ensure(flat)
+        b.eri_build()
+        if self.distributed and self.world > 1 and self.kw["storage"] == _lib.STORAGE_INCORE:
+            from .parallel import reduce_scatter_supermatrix
+
+            reduce_scatter_supermatrix(b, self.rank, self.world)
+
+    def build_g(self, D):
+        G = self.builder.build_g(D)
+        if self.distributed and self.world > 1:
+            from .parallel import allreduce_host_matrix
+
+            G = allreduce_host_matrix(G)
+        return G

@@ -1,0 +1,73 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed (NCCL over NVLink) for the exchange.
+
+The path shards naturally: shell-quartet tiles are dealt round-robin to ranks
+inside the kernels (`fock_opts.rank/world`), every rank accumulates a partial result, and there is
+exactly one exchange step per SCF iteration -- an all-reduce of the N x N partial G.  In-core mode
+additionally reduce-scatters the packed supermatrix once after the build so that each rank streams
+only 1/world of it per iteration.
+"""
+from __future__ import annotations
+
+from typing import List, Tuple
+
+import numpy as np
+
+
+def digest_ranges(n_elements: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous element ranges of the packed supermatrix, one per rank, equal up to padding
+    (the layout NCCL reduce-scatter produces)."""
+    chunk = (n_elements + world - 1) // world
+    return [(min(r * chunk, n_elements), min((r + 1) * chunk, n_elements)) for r in range(world)]
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ wrapper so torch can view a raw device buffer."""
+
+    def __init__(self, ptr: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
+
+
+def device_view(ptr: int, n: int, device=None):
+    import torch
+
+    return torch.as_tensor(_DevArray(ptr, n), device=device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+
+
+def reduce_scatter_supermatrix(builder, rank: int, world: int):
+    """Sum the per-rank partial supermatrices; rank r keeps elements digest_ranges()[r]."""
+    import torch
+    import torch.distributed as dist
+
+    ptr, n_padded = builder.supermatrix_device()
+    n = builder._L.fock_packed_len(builder.n)
+    chunk = (n + world - 1) // world
+    assert n_padded >= chunk * world, "supermatrix buffer is not padded for this world size"
+    full = device_view(ptr, chunk * world)
+    torch.cuda.synchronize()
+    out = full[rank * chunk : (rank + 1) * chunk]
+    dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM)
+    torch.cuda.synchronize()
+    begin, end = digest_ranges(n, world)[rank]
+    builder.set_digest_range(begin, end)
+
+
+def allreduce_host_matrix(G: np.ndarray) -> np.ndarray:
+    """Sum a host matrix over ranks (NCCL needs a device tensor; gloo works on the host)."""
+    import torch
+    import torch.distributed as dist
+
+    if dist.get_backend() == "nccl":
+        t = torch.from_numpy(np.ascontiguousarray(G)).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.cpu().numpy().reshape(G.shape)
+    t = torch.from_numpy(np.ascontiguousarray(G).copy())
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.numpy().reshape(G.shape)
+
+
+def allreduce_device(g_tensor):
+    """The per-iteration exchange for device-resident G: one all-reduce of N*N doubles."""
+    import torch.distributed as dist
+
+    dist.all_reduce(g_tensor, op=dist.ReduceOp.SUM)
+    return g_tensor

@@ -1,0 +1,158 @@
+/*
+ * fock_b200.h -- C ABI of the B200-native ERI + Fock-build path for fock-rs.
+ *
+ * The reference (iggedi-ig-ig/fock-rs) is pure Rust with no FFI/plugin seam of its own
+ * (SURVEY.md section 8b).  This header is the seam a maintainer binds from Rust (see
+ * INTEGRATION.md for the `extern "C"` block and the three call sites in scf/src/lib.rs).
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference checkout).
+ *
+ * Conventions: plain C, opaque handle, int status (0 = OK), caller-owned HOST buffers unless
+ * the name says `_device`, no callbacks, nothing thrown across the boundary.  A context is
+ * used from one thread at a time (the reference calls this path from one thread too).
+ * All matrices are column-major N x N doubles exactly as nalgebra's DMatrix<f64> stores
+ * them (scf/src/lib.rs uses DMatrix throughout).
+ *
+ * There is no CPU fallback: every compute entry point returns FOCK_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef FOCK_B200_H
+#define FOCK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FOCK_B200_ABI_VERSION 1
+
+typedef struct fock_ctx fock_ctx;
+
+/* Status codes.  The reference panics / returns None where these are nonzero:
+ *   FOCK_ERR_BOYS_ORDER  <->  assert!(n <= MAX_TABULATED_N) in boys/src/lib.rs:59-62 */
+enum {
+    FOCK_OK = 0,
+    FOCK_ERR_BAD_ARG = 1,
+    FOCK_ERR_BOYS_ORDER = 2,
+    FOCK_ERR_CUDA = 3,
+    FOCK_ERR_OOM = 4,
+    FOCK_ERR_STATE = 5,
+    FOCK_ERR_UNSUPPORTED = 6
+};
+
+/* Structure-of-arrays view of `&[ContractedGaussian]` (basis/src/contracted_gaussian.rs:9-15,
+ * basis/src/primitives.rs:7-11), one entry per basis FUNCTION in the reference's order
+ * (scf/src/lib.rs:79-83).  Built by the Rust shim through the public accessors position(),
+ * primitives(), angular(), exponent(), coefficient().  `coefficient` already carries the
+ * primitive norm (GaussianPrimitive::new, primitives.rs:41-48).  Shell structure is
+ * reconstructed inside fock_create (the reference discards it, basis_set/src/lib.rs:84). */
+typedef struct {
+    int32_t n_basis;            /* N */
+    const double *center;       /* [N][3] bohr */
+    const int32_t *angular;     /* [N][3] (l,m,n) as GaussianPrimitive.angular */
+    const int32_t *prim_offset; /* [N+1] */
+    const double *exponent;     /* [prim_offset[N]] */
+    const double *coefficient;  /* [prim_offset[N]] */
+} fock_basis;
+
+/* mode bits (0 = reproduce the reference's arithmetic) */
+#define FOCK_MODE_FAITHFUL 0
+#define FOCK_MODE_BOYS_ACCURATE 1 /* accurate Boys function instead of boys/src/lib.rs:58-81 (F1) */
+#define FOCK_MODE_FIX_R 2         /* restore the (t-1) factor of basis/src/utils.rs:98-105 (F2)  */
+#define FOCK_MODE_ACCURATE 3
+
+/* screen */
+#define FOCK_SCREEN_REFERENCE 0 /* basis/src/electron_tensor.rs:129-155: zero unless sqrt((ij|ij)(kl|kl)) > 1e-6 */
+#define FOCK_SCREEN_OFF 1       /* every unique integral evaluated */
+#define FOCK_SCREEN_SCHWARZ 2   /* same estimate, user threshold `tau` */
+
+/* storage */
+#define FOCK_STORAGE_INCORE 0 /* symmetry-packed tensor resident in HBM, streamed every fock_build_g */
+#define FOCK_STORAGE_DIRECT 1 /* integrals regenerated and digested inside every fock_build_g */
+
+typedef struct {
+    int32_t mode;
+    int32_t screen;
+    double tau;       /* FOCK_SCREEN_SCHWARZ threshold */
+    int32_t storage;
+    int32_t device;   /* CUDA ordinal; -1 = current device */
+    int32_t rank;     /* this process's shard of the shell-quartet tiles, 0 <= rank < world */
+    int32_t world;    /* number of shards (1 = whole job) */
+    int32_t keep_eri; /* in-core: also keep the raw (ij|kl) tensor for fock_eri_get/export (default 1) */
+    int32_t kernel;   /* 0 = class kernels (default), 1 = force the generic per-function kernel */
+} fock_opts;
+
+void fock_default_opts(fock_opts *opts);
+
+/* Upload the basis once, regroup it into shells / angular-momentum classes, build primitive-pair
+ * data.  Replaces the `&[ContractedGaussian]` argument handling of
+ * ElectronTensor::from_basis (basis/src/electron_tensor.rs:81-87). */
+int fock_create(const fock_basis *basis, const fock_opts *opts, fock_ctx **out);
+
+/* ElectronTensor::from_basis (basis/src/electron_tensor.rs:81-176): diagonal pass, then all
+ * unique integrals with the screening rule of `opts.screen`; in-core mode also forms the
+ * J-1/2K supermatrix that replaces the `electron_terms` precompute (scf/src/lib.rs:167-173).
+ * In direct mode only the diagonal (screening estimates) is computed. */
+int fock_eri_build(fock_ctx *ctx);
+
+/* `tensor[(i,j,k,l)]` -- Index<(usize,usize,usize,usize)> for ElectronTensor
+ * (basis/src/electron_tensor.rs:179-187).  Needs in-core storage with keep_eri. */
+int fock_eri_get(fock_ctx *ctx, int32_t i, int32_t j, int32_t k, int32_t l, double *value);
+
+/* All unique integrals in canonical order: slot tri(tri(x,y),tri(z,w)), x>=y, z>=w,
+ * tri(x,y)>=tri(z,w), tri(a,b)=a(a+1)/2+b -- the canonical representative of
+ * IntegralIndex::correct_order (basis/src/electron_tensor.rs:37-51).  `n` must equal
+ * fock_packed_len(N). */
+int fock_eri_export_packed(fock_ctx *ctx, double *host, size_t n);
+size_t fock_packed_len(int32_t n_basis);
+
+/* BasisFunction::electron_repulsion_int(a,b,c,d) (basis/src/lib.rs:41,
+ * basis/src/contracted_gaussian.rs:264-318) for a batch of basis-function quartets
+ * `quartets[n][4]`; no screening.  Evaluated on the GPU by the generic per-function kernel. */
+int fock_eri_batch(fock_ctx *ctx, const int32_t *quartets, size_t n, double *values);
+
+/* The per-iteration G build, scf/src/lib.rs:177-185 (inside utils::hermitian, scf/src/utils.rs:25-28):
+ *   G_ij = sum_xy D[(x,y)] * ((ij|xy) - 1/2 (ix|jy)),   G symmetric.
+ * D must be symmetric (the reference's density is, by construction).  With world > 1 the
+ * result is this rank's PARTIAL G; the caller sums partials (one all-reduce of N*N doubles). */
+int fock_build_g(fock_ctx *ctx, const double *D, double *G);
+
+/* Same with device-resident D and G (N*N doubles each) on the context's stream. */
+int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev);
+
+/* One-electron matrices S, T, V (BasisFunction::overlap_int / kinetic_int /
+ * nuclear_attraction_int, basis/src/contracted_gaussian.rs:209-262; scf/src/lib.rs:118-128),
+ * `nuclei_pos[n][3]`, `nuclei_charge[n]` = PointCharge (basis/src/lib.rs:8-12). */
+int fock_one_electron(fock_ctx *ctx, int32_t n_nuclei, const double *nuclei_pos, const double *nuclei_charge,
+                      double *S, double *T, double *V);
+
+/* Use a caller-provided cudaStream_t for all launches (NULL = the context's own stream). */
+int fock_set_stream(fock_ctx *ctx, void *cuda_stream);
+
+/* Multi-process in-core plumbing (one process per GPU): the supermatrix buffer, so the host
+ * side can reduce-scatter it with its collective library, then the element range
+ * [begin, end) of the packed supermatrix this rank streams in fock_build_g. */
+int fock_supermatrix_device(fock_ctx *ctx, void **dev_ptr, size_t *n_elements);
+int fock_set_digest_range(fock_ctx *ctx, size_t begin, size_t end);
+
+/* Timings of the last fock_eri_build / fock_build_g in milliseconds (CUDA events):
+ *   [0] pair/diagonal pass  [1] ERI class kernels  [2] supermatrix formation
+ *   [3] last G build (device part)  [4] last G build incl. host<->device copies */
+int fock_timings(fock_ctx *ctx, double *ms, int32_t n);
+
+/* Counters: [0] N  [1] shells  [2] shell pairs  [3] unique shell quartets (unscreened)
+ *   [4] shell quartets evaluated by the last build / direct G  [5] primitive quartets evaluated
+ *   [6] kernel launches of the last fock_eri_build  [7] kernel launches of the last fock_build_g
+ *   [8] model FP64 flops of the quartets evaluated (SURVEY.md section 8d formula) */
+int fock_stats(fock_ctx *ctx, int64_t *out, int32_t n);
+
+const char *fock_last_error(fock_ctx *ctx); /* ctx may be NULL: last fock_create error */
+void fock_destroy(fock_ctx *ctx);
+int fock_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOCK_B200_H */
