@@ -1,0 +1,384 @@
+#!/usr/bin/env python3
+"""bench.py -- ERI + Fock-build benchmark (BASELINE.json metric) for the B200 path and, with
+`--impl reference`, for the reference's CPU algorithm on the host cores.
+
+One "step" = one complete pass of the hot path for one SCF iteration's worth of input:
+  in-core : ElectronTensor::from_basis (diagonal pass, all surviving shell quartets, supermatrix)
+            + one G = J - K/2 build from a density                (nothing cached between steps)
+  direct  : one fused ERI -> J/K build from a density
+`value` = unique shell quartets of the workload / step time (whole job, all ranks), with the density
+and the result resident in HBM; `e2e` = the same through the C ABI's host-buffer entry points
+(density copied host->device and G device->host inside the timed region every step).
+
+Launch:  python bench.py [--gpus N --steps K --warmup W]   (N>1: under torchrun, one rank per GPU)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+WORKLOADS = {
+    # name: (description, molecule key, basis)
+    "benzene": ("Benzene RHF 6-31G (66 bf)", "benzene", "6-31G"),
+    "w16": ("(H2O)16 water cluster 6-31G (208 bf)", "w16", "6-31G"),
+    "alkane40": ("Linear alkane C40H82 6-31G (524 bf)", "alkane40", "6-31G"),
+    "w32": ("(H2O)32 6-31G** (800 bf Cartesian)", "w32", "6-31G**"),
+    "water": ("H2O RHF STO-3G (7 bf)", "water", "STO-3G"),
+}
+
+
+def load_flat(workload):
+    from helpers import flat_for
+
+    _, mol, basis = WORKLOADS[workload]
+    return flat_for(mol, basis)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU baseline: the oracle (a C restatement of the reference's algorithm; the Rust reference cannot
+# be built in this image) on a bounded sample of the same workload, all host threads.
+
+
+def count_surviving(diag, thr=1e-6):
+    """Number of unordered pairs {xy, zw}, xy != zw, with sqrt(d_xy * d_zw) > thr (the reference's cut)."""
+    d = np.sort(np.asarray(diag))[::-1]
+    n = d.size
+    total = 0
+    step = 2048
+    for i0 in range(0, n, step):
+        blk = d[i0 : i0 + step]
+        est = np.sqrt(np.outer(blk, d))
+        ok = est > thr
+        # count j > i only
+        idx = np.arange(i0, min(i0 + step, n))[:, None]
+        total += int(np.count_nonzero(ok & (np.arange(n)[None, :] > idx)))
+    return total
+
+
+def cpu_baseline(workload, screen_ref, budget_s, quartets_unique):
+    import oracle
+
+    flat = load_flat(workload)
+    ob = oracle.OracleBasis.from_flat(flat)
+    n = flat.n_basis
+    npair = n * (n + 1) // 2
+    flags = oracle.FAITHFUL if screen_ref else oracle.NO_CUT
+    threads = oracle.num_threads()
+    t0 = time.perf_counter()
+    diag = oracle.diagonal(ob, flags, fast=True)  # screening estimates (tabulated evaluator: only to pick the sample)
+    n_off_total = npair * (npair - 1) // 2
+    n_surv = count_surviving(diag) if screen_ref else n_off_total
+    # pilot: a handful of rows to size the sample
+    pilot_rows = max(threads, 8)
+    stride = max(1, npair // pilot_rows)
+    t1 = time.perf_counter()
+    nev, _ = oracle.sample_rows(ob, diag, stride // 2, stride, pilot_rows, flags, fast=False)
+    dt = time.perf_counter() - t1
+    rate = max(nev, 1) / max(dt, 1e-6)
+    rows = pilot_rows
+    for _ in range(4):  # grow the sample until it costs about budget_s of wall time
+        rows = int(min(npair, max(rows + 1, budget_s * rate / max(n_surv / npair, 1.0))))
+        stride = max(1, npair // rows)
+        t1 = time.perf_counter()
+        nev, checksum = oracle.sample_rows(ob, diag, stride // 2, stride, rows, flags, fast=False)
+        dt = time.perf_counter() - t1
+        rate = max(nev, 1) / max(dt, 1e-6)
+        if dt >= 0.6 * budget_s or rows >= npair:
+            break
+    t_eri = (n_surv + npair) / rate  # + the diagonal pass
+    # G build: the reference's N^4/2 loop, timed on a zero tensor of the right size when it fits
+    t1 = time.perf_counter()
+    if n <= 260:
+        packed = np.zeros(oracle.packed_len(n))
+        D = np.zeros((n, n))
+        oracle.build_g(packed, n, D, parallel=True)
+        t_g = time.perf_counter() - t1
+        g_note = f"G build timed in full at N={n} (OpenMP, {threads} threads)"
+    else:
+        m = 120
+        packed = np.zeros(oracle.packed_len(m))
+        oracle.build_g(packed, m, np.zeros((m, m)), parallel=True)
+        t_g = (time.perf_counter() - t1) * (n / m) ** 4
+        g_note = f"G build timed at N={m} and scaled by (N/{m})^4"
+    t_total = t_eri + t_g
+    return {
+        "value": quartets_unique / t_total,
+        "unit": "shell_quartets/s",
+        "cores": threads,
+        "kind": "port",
+        "sample": (f"{nev} contracted integrals of {n_surv} surviving ({'reference 1e-6 cut' if screen_ref else 'no cut'}) from {rows} evenly "
+                   f"strided canonical rows, un-memoised reference recursion, {dt:.1f} s -> {rate:.3e} integrals/s; whole-job ERI time "
+                   f"extrapolated to {t_eri:.1f} s; {g_note}: {t_g:.2f} s"),
+        "integrals_per_s": rate,
+        "eri_s_extrapolated": t_eri,
+        "g_s": t_g,
+        "s_per_step": t_total,
+        "sample_wall_s": time.perf_counter() - t0,
+        "checksum": checksum,
+    }
+
+
+def unique_shell_quartets(flat):
+    """Unique shell quartets of the workload (s and p of an SP shell are separate shells)."""
+    shells = 0
+    prev = None
+    for i in range(flat.n_basis):
+        key = (tuple(flat.center[i]), int(flat.angular[i].sum()), tuple(flat.exponent[flat.prim_offset[i] : flat.prim_offset[i + 1]]))
+        if key != prev:
+            shells += 1
+            prev = key
+    sp = shells * (shells + 1) // 2
+    return sp * (sp + 1) // 2, shells
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    flat = load_flat(args.workload)
+    nq, _ = unique_shell_quartets(flat)
+    screen_ref = args.screen == "ref"
+    vals = []
+    last = None
+    for i in range(args.warmup + args.steps):
+        budget = 2.0 if i < args.warmup else args.ref_budget
+        last = cpu_baseline(args.workload, screen_ref, budget, nq)
+        if i >= args.warmup:
+            vals.append(last)
+    t = float(np.mean([v["s_per_step"] for v in vals]))
+    value = nq / t
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "shell_quartets/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_dict(args, flat),
+        "cpu_baseline": {k: last[k] for k in ("kind", "cores", "sample")} | {"value": value, "unit": "shell_quartets/s"},
+        "e2e": {"value": value, "unit": "shell_quartets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+METRIC = "ERI+Fock-build unique shell quartets/s per SCF iteration (ms_per_step = ERI+Fock-build time per SCF iteration)"
+
+
+def config_dict(args, flat):
+    return {
+        "workload": WORKLOADS[args.workload][0],
+        "n_basis": flat.n_basis,
+        "storage": args.storage,
+        "mode": args.mode,
+        "screening": "reference 1e-6 cut (basis/src/electron_tensor.rs:134-155)" if args.screen == "ref" else "off",
+        "l2": "inputs larger than L2 (packed tensor) " if flat.n_basis >= 150 else "L2 flushed between timed steps (256 MiB write)",
+        "parallelism": f"shell-quartet tiles sharded over {args.gpus} rank(s); one all-reduce of G per step",
+    }
+
+
+def run_ours(args):
+    import torch
+
+    from fock_rs_b200 import _lib
+    from fock_rs_b200.fock import FockBuilder
+    from fock_rs_b200 import parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    flat = load_flat(args.workload)
+    n = flat.n_basis
+    nq, nshell = unique_shell_quartets(flat)
+    mode = _lib.MODE_FAITHFUL if args.mode == "faithful" else _lib.MODE_ACCURATE
+    screen = _lib.SCREEN_REFERENCE if args.screen == "ref" else _lib.SCREEN_OFF
+    storage = _lib.STORAGE_INCORE if args.storage == "incore" else _lib.STORAGE_DIRECT
+    b = FockBuilder(flat, mode=mode, screen=screen, storage=storage, device=local, rank=rank, world=world, keep_eri=False)
+    stream = torch.cuda.current_stream()
+    b.set_stream(stream.cuda_stream)
+    rng = np.random.default_rng(20261017)
+    Dh = rng.uniform(-1.0, 1.0, (n, n))
+    Dh = np.asfortranarray(0.5 * (Dh + Dh.T))
+    D = torch.from_numpy(np.ascontiguousarray(Dh.T)).cuda()  # column-major image
+    G = torch.empty_like(D)
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda") if n < 150 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_device():
+        b.eri_build()
+        if world > 1 and storage == _lib.STORAGE_INCORE:
+            parallel.reduce_scatter_supermatrix(b, rank, world)
+        b.build_g_device(D.data_ptr(), G.data_ptr())
+        if world > 1:
+            parallel.allreduce_device(G)
+
+    def step_host():
+        b.eri_build()
+        if world > 1 and storage == _lib.STORAGE_INCORE:
+            parallel.reduce_scatter_supermatrix(b, rank, world)
+        g = b.build_g(Dh)
+        if world > 1:
+            g = parallel.allreduce_host_matrix(g)
+        return g
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s, e in evs:
+            if flush is not None:
+                flush.fill_(1.0)
+            s.record(stream)
+            fn()
+            e.record(stream)
+        torch.cuda.synchronize()
+        return sum(s.elapsed_time(e) for s, e in evs)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+    with ClockSampler(local) as clocks:
+        barrier()
+        t_dev_ms = timed(step_device, args.steps)
+        barrier()
+    tm = b.timings()
+    st = b.stats()
+    for _ in range(2):
+        step_host()
+    barrier()
+    t_host_ms = timed(step_host, args.steps)
+    barrier()
+    g_host = step_host()
+    # max over ranks
+    if dist is not None:
+        t = torch.tensor([t_dev_ms, t_host_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev_ms, t_host_ms = float(t[0]), float(t[1])
+    ms_step = t_dev_ms / args.steps
+    ms_e2e = t_host_ms / args.steps
+    fp64_peak = b.measure_fp64_peak()
+    hbm_peak, peak_src = measured_peaks()
+    nelem = b._L.fock_packed_len(n)
+    # sanity: device and host paths agree
+    torch.cuda.synchronize()
+    agree = float(np.max(np.abs(G.cpu().numpy().T - g_host)))
+
+    if rank == 0:
+        eri_tf = st["model_flops"] / max(tm["eri_ms"], 1e-9) * 1e-9 / 1e3 if tm["eri_ms"] > 0 else 0.0
+        g_gbs = 8.0 * nelem / world / max(tm["g_device_ms"], 1e-9) * 1e-6
+        parts = {"diag_ms": tm["diag_ms"], "eri_ms": tm["eri_ms"], "supermatrix_ms": tm["supermatrix_ms"], "g_ms": tm["g_device_ms"]}
+        dominant = max(parts, key=parts.get)
+        roof_eri = {"bound": "fp64", "achieved": eri_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": eri_tf / fp64_peak if fp64_peak else None,
+                    "traffic": None, "kernel": "eri_class_kernel<*> (all class launches of one build, incl. host tile-table gaps)",
+                    "note": "model flops of the quartets evaluated (SURVEY.md 8d formula) / time between the events bracketing the class launches; peak = DFMA-chain probe measured in this run"}
+        roof_g = {"bound": "hbm", "achieved": g_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": g_gbs / hbm_peak, "traffic": None,
+                  "kernel": "symv_packed_kernel (+ pack/unpack)", "note": f"8 B per stored supermatrix element per rank / device time of one G build; peak = {peak_src}"}
+        line = {
+            "metric": METRIC, "value": nq / (ms_step * 1e-3), "unit": "shell_quartets/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, flat),
+            "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "shell_quartets/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 8 * n * n, "d2h_bytes_per_step": 8 * n * n},
+            "gpu_launches": int((st["launches_build"] + st["launches_g"]) * args.steps),
+            "clocks": clocks.summary(),
+            "roofline": roof_g if dominant == "g_ms" else roof_eri,
+            "roofline_eri": roof_eri, "roofline_digest": roof_g,
+            "breakdown_ms": parts, "dominant": dominant,
+            "stats": {"shells": nshell, "shell_quartets_unique": nq, "class_shell_quartets_evaluated": st["shell_quartets_evaluated"],
+                      "prim_quartets_evaluated": st["prim_quartets_evaluated"], "model_flops": st["model_flops"], "device_vs_host_path_max_abs_diff": agree},
+            "fp64_peak_tflops_measured": fp64_peak,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.workload, args.screen == "ref", args.cpu_budget, nq).items() if k not in ("checksum",)}
+        print(json.dumps(line))
+    b.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="w16", choices=sorted(WORKLOADS))
+    ap.add_argument("--storage", default="incore", choices=["incore", "direct"])
+    ap.add_argument("--screen", default="ref", choices=["ref", "off"])
+    ap.add_argument("--mode", default="faithful", choices=["faithful", "accurate"])
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--ref-budget", type=float, default=12.0, help="seconds of CPU work per step of --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

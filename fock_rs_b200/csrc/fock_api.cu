@@ -309,6 +309,9 @@ int fock_eri_build(fock_ctx *ctx) {
         FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_V, 0, ctx->nelem * sizeof(double), st));
         FOCK_CUDA_TRY(ctx, cudaMemsetAsync(cs->d_counter, 0, sizeof(unsigned long long), st));
         const double thr = screen_threshold(ctx->opts);
+        diag_to_tensor_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(ctx->d_diag, ctx->npair, ctx->opts.rank,
+                                                                                  ctx->opts.world, ctx->d_V);
+        launches += 1;
         if (!ctx->shells.pairs.empty()) {
             StoreSink sink{ctx->d_V, ctx->d_diag, thr, ctx->opts.screen};
             std::string err;
@@ -575,6 +578,28 @@ int fock_set_digest_range(fock_ctx *ctx, size_t begin, size_t end) {
     if (!ctx || begin > end || end > ctx->nelem) return FOCK_ERR_BAD_ARG;
     ctx->digest_begin = begin;
     ctx->digest_end = end;
+    return FOCK_OK;
+}
+
+int fock_measure_fp64_peak(fock_ctx *ctx, double *tflops) {
+    if (!ctx || !tflops) return FOCK_ERR_BAD_ARG;
+    FOCK_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    FOCK_CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    cudaStream_t st = ctx->stream;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_A], st));
+        dfma_peak_kernel<<<blocks, 256, 0, st>>>(ctx->d_diag, iters, 1.0 + rep);
+        FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_B], st));
+        FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[EV_A], ctx->ev[EV_B]);
+        const double flops = 2.0 * 8.0 * 16.0 * (double)iters * 256.0 * (double)blocks;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    *tflops = best;
     return FOCK_OK;
 }
 

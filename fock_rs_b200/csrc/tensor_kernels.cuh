@@ -31,21 +31,26 @@ __global__ void generic_tensor_kernel(BasisDev bs, BoysTables bt, int mode, cons
     untri(e, xy, zw);
     untri(xy, x, y);
     untri(zw, z, w);
+    if (xy == zw) return;  // diagonal slots: diag_to_tensor_kernel
     if (skip_class && bf_class_ok[x] && bf_class_ok[y] && bf_class_ok[z] && bf_class_ok[w]) return;
-    double v;
-    if (xy == zw) {
-        v = diag[xy];
-    } else {
-        bool keep = true;
-        if (screen != 1) keep = sqrt(diag[xy] * diag[zw]) > thr;
-        if (keep) {
-            v = eri_function_quartet(bs, (int)x, (int)y, (int)z, (int)w, mode, bt);
-            atomicAdd(n_eval, 1ULL);
-        } else {
-            v = 0.0;
-        }
+    double v = 0.0;
+    bool keep = true;
+    if (screen != 1) keep = sqrt(diag[xy] * diag[zw]) > thr;
+    if (keep) {
+        v = eri_function_quartet(bs, (int)x, (int)y, (int)z, (int)w, mode, bt);
+        atomicAdd(n_eval, 1ULL);
     }
     V[e] = v;
+}
+
+// ---- the diagonal pass's results go into the tensor unconditionally (the reference computes
+// (ij|ij) before and outside the screened loop, electron_tensor.rs:90-101).  With several ranks each
+// diagonal slot is written by exactly one of them so that partial tensors sum correctly.
+__global__ void diag_to_tensor_kernel(const double *__restrict__ diag, size_t npair, int rank, int world,
+                                      double *__restrict__ V) {
+    const size_t xy = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (xy >= npair || (int)(xy % (size_t)world) != rank) return;
+    V[tri(xy, xy)] = diag[xy];
 }
 
 // ---- batch of arbitrary function quartets (fock_eri_batch)
@@ -173,6 +178,21 @@ __global__ void __launch_bounds__(kSymvThreads) symv_packed_kernel(const double 
         for (int w = 0; w < kSymvThreads / 32; ++w) v += s_red[w][tid];
         if (v != 0.0) atomicAdd(y + r0 + tid, v);
     }
+}
+
+// ---- FP64 FMA peak probe: 8 independent register chains per thread.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0 - 1e-9, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;  // keep the chains alive
 }
 
 // ---- one-electron matrices (off the hot path).  One thread per i<=j.

@@ -137,6 +137,12 @@ class FockBuilder:
     def set_digest_range(self, begin: int, end: int):
         self._check(self._L.fock_set_digest_range(self._ctx, begin, end))
 
+    def measure_fp64_peak(self) -> float:
+        """Sustained DFMA rate of this GPU in TFLOP/s (roofline denominator for the ERI kernels)."""
+        v = C.c_double()
+        self._check(self._L.fock_measure_fp64_peak(self._ctx, C.byref(v)))
+        return v.value
+
     def timings(self) -> dict:
         ms = (C.c_double * 8)()
         self._check(self._L.fock_timings(self._ctx, ms, 8))

@@ -148,6 +148,11 @@ int fock_timings(fock_ctx *ctx, double *ms, int32_t n);
  *   [8] model FP64 flops of the quartets evaluated (SURVEY.md section 8d formula) */
 int fock_stats(fock_ctx *ctx, int64_t *out, int32_t n);
 
+/* Measurement aid (no reference counterpart): sustained FP64 FMA rate of this GPU from a
+ * register-resident DFMA-chain kernel, in TFLOP/s (2 flops per FMA).  It is the denominator the
+ * ERI kernels' "fraction of FP64 peak" is quoted against (MEASURED_PEAKS.json has no FP64 figure). */
+int fock_measure_fp64_peak(fock_ctx *ctx, double *tflops);
+
 const char *fock_last_error(fock_ctx *ctx); /* ctx may be NULL: last fock_create error */
 void fock_destroy(fock_ctx *ctx);
 int fock_abi_version(void);
