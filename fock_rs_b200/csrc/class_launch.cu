@@ -1,7 +1,8 @@
-// class_launch.cu -- host side of the shell-class ERI kernels: diagonal pass, sublist sorting,
-// tile tables for the (bra sublist, ket sublist) launches, kernel dispatch.
+// class_launch.cu -- host side of the shell-class ERI kernels: diagonal pass, sublist sorting
+// (device-side permutation of the primitive-pair tables), the job / warp-tile plan, kernel dispatch.
 #include <algorithm>
 #include <cmath>
+#include <numeric>
 
 #include "../../include/fock_b200.h"
 #include "class_launch.h"
@@ -11,72 +12,97 @@ namespace fock {
 
 namespace {
 
-template <int LA, int LB, int LC, int LD, int KC0, int KCN, bool DIAG, class Sink>
+const int kClsLA[3] = {0, 1, 1}, kClsLB[3] = {0, 0, 1};
+
+template <int LA, int LB, int LC, int LD, int KC0, int KCN, class Sink>
 void launch_mode(const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, size_t smem, cudaStream_t st) {
     const bool acc = mode & FOCK_MODE_BOYS_ACCURATE_BIT, fix = mode & FOCK_MODE_FIX_R_BIT;
     if (!acc && !fix)
-        eri_class_kernel<LA, LB, LC, LD, false, false, KC0, KCN, DIAG, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
+        eri_class_kernel<LA, LB, LC, LD, false, false, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
     else if (!acc && fix)
-        eri_class_kernel<LA, LB, LC, LD, false, true, KC0, KCN, DIAG, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
+        eri_class_kernel<LA, LB, LC, LD, false, true, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
     else if (acc && !fix)
-        eri_class_kernel<LA, LB, LC, LD, true, false, KC0, KCN, DIAG, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
+        eri_class_kernel<LA, LB, LC, LD, true, false, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
     else
-        eri_class_kernel<LA, LB, LC, LD, true, true, KC0, KCN, DIAG, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
+        eri_class_kernel<LA, LB, LC, LD, true, true, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
 }
 
-// Returns the number of kernel launches issued.
-template <bool DIAG, class Sink>
+template <class Sink>
 int launch_class(int cb, int ck, const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, cudaStream_t st) {
-    const size_t smem = DIAG ? 0 : (size_t)cl.Kab * pair_fields(cb) * sizeof(double);
-    const int key = cb * 3 + ck;
-    switch (key) {
-        case 0: launch_mode<0, 0, 0, 0, 0, 1, DIAG>(cl, sink, mode, grid, smem, st); return 1;
-        case 3: if constexpr (!DIAG) launch_mode<1, 0, 0, 0, 0, 1, DIAG>(cl, sink, mode, grid, smem, st); return 1;
-        case 4: launch_mode<1, 0, 1, 0, 0, 3, DIAG>(cl, sink, mode, grid, smem, st); return 1;
-        case 6: if constexpr (!DIAG) launch_mode<1, 1, 0, 0, 0, 1, DIAG>(cl, sink, mode, grid, smem, st); return 1;
-        case 7: if constexpr (!DIAG) launch_mode<1, 1, 1, 0, 0, 3, DIAG>(cl, sink, mode, grid, smem, st); return 1;
+    const size_t smem = (size_t)cl.max_bra_doubles * kClassWarps * sizeof(double);
+    switch (cb * 3 + ck) {
+        case 0: launch_mode<0, 0, 0, 0, 0, 1>(cl, sink, mode, grid, smem, st); return 1;
+        case 3: launch_mode<1, 0, 0, 0, 0, 1>(cl, sink, mode, grid, smem, st); return 1;
+        case 4: launch_mode<1, 0, 1, 0, 0, 3>(cl, sink, mode, grid, smem, st); return 1;
+        case 6: launch_mode<1, 1, 0, 0, 0, 1>(cl, sink, mode, grid, smem, st); return 1;
+        case 7: launch_mode<1, 1, 1, 0, 0, 3>(cl, sink, mode, grid, smem, st); return 1;
         case 8:  // (pp|pp): 81 accumulators do not fit one thread's registers -> three ket-component slices
-            launch_mode<1, 1, 1, 1, 0, 3, DIAG>(cl, sink, mode, grid, smem, st);
-            launch_mode<1, 1, 1, 1, 3, 3, DIAG>(cl, sink, mode, grid, smem, st);
-            launch_mode<1, 1, 1, 1, 6, 3, DIAG>(cl, sink, mode, grid, smem, st);
+            launch_mode<1, 1, 1, 1, 0, 3>(cl, sink, mode, grid, smem, st);
+            launch_mode<1, 1, 1, 1, 3, 3>(cl, sink, mode, grid, smem, st);
+            launch_mode<1, 1, 1, 1, 6, 3>(cl, sink, mode, grid, smem, st);
             return 3;
         default: return 0;
     }
 }
 
-const int kClsLA[3] = {0, 1, 1}, kClsLB[3] = {0, 0, 1};
+template <int LA, int LB, int KC0, int KCN>
+void launch_diag_mode(const DiagLaunch &dl, const DiagSink &sink, int mode, dim3 grid, cudaStream_t st) {
+    const bool acc = mode & FOCK_MODE_BOYS_ACCURATE_BIT, fix = mode & FOCK_MODE_FIX_R_BIT;
+    if (!acc && !fix)
+        eri_diag_kernel<LA, LB, false, false, KC0, KCN><<<grid, kClassThreads, 0, st>>>(dl, sink);
+    else if (!acc && fix)
+        eri_diag_kernel<LA, LB, false, true, KC0, KCN><<<grid, kClassThreads, 0, st>>>(dl, sink);
+    else if (acc && !fix)
+        eri_diag_kernel<LA, LB, true, false, KC0, KCN><<<grid, kClassThreads, 0, st>>>(dl, sink);
+    else
+        eri_diag_kernel<LA, LB, true, true, KC0, KCN><<<grid, kClassThreads, 0, st>>>(dl, sink);
+}
+
+// sorted tables from the natural-order master: position i of a sublist takes natural pair perm[i]
+__global__ void permute_pairs_kernel(const double *__restrict__ bra_nat, const int *__restrict__ meta_nat,
+                                     const int *__restrict__ perm, int n, int K, int nf, int npad,
+                                     double *__restrict__ bra, double *__restrict__ ket, int *__restrict__ meta) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const int src = perm[i];
+    const int len = K * nf;
+    for (int e = threadIdx.x; e < len; e += blockDim.x) {
+        const double v = bra_nat[(size_t)src * len + e];
+        bra[(size_t)i * len + e] = v;
+        ket[(size_t)e * npad + i] = v;  // e = ij*nf + f
+    }
+    if (threadIdx.x < 2) meta[2 * i + threadIdx.x] = meta_nat[2 * src + threadIdx.x];
+}
 
 }  // namespace
 
-int ClassEngine::upload_tables(std::string &err) {
+int ClassEngine::upload_master(std::string &err) {
     std::vector<double> bra, ket;
     std::vector<int> meta;
     build_pair_tables(*sd, bra, ket, meta);
-    auto re = [&](void **p, size_t bytes) {
-        if (*p) cudaFree(*p);
-        *p = nullptr;
-        return cudaMalloc(p, bytes ? bytes : 8);
-    };
+    nat_ids.clear();
+    for (const Sublist &s : sd->sublists) nat_ids.push_back(s.pair_ids);
     cudaError_t e;
-    if ((e = re((void **)&dev->d_bra, bra.size() * 8)) != cudaSuccess ||
-        (e = re((void **)&dev->d_ket, ket.size() * 8)) != cudaSuccess ||
-        (e = re((void **)&dev->d_meta, meta.size() * 4)) != cudaSuccess) {
+    auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 8); };
+    if ((e = alloc((void **)&d_bra_nat, bra.size() * 8)) != cudaSuccess || (e = alloc((void **)&dev->d_bra, bra.size() * 8)) != cudaSuccess ||
+        (e = alloc((void **)&dev->d_ket, ket.size() * 8)) != cudaSuccess || (e = alloc((void **)&d_meta_nat, meta.size() * 4)) != cudaSuccess ||
+        (e = alloc((void **)&dev->d_meta, meta.size() * 4)) != cudaSuccess || (e = alloc((void **)&d_perm, meta.size() * 2 + 8)) != cudaSuccess) {
         err = std::string("pair tables: ") + cudaGetErrorString(e);
         return 1;
     }
+    std::vector<int> sbf(sd->shells.size() * 6);
+    for (size_t s = 0; s < sd->shells.size(); ++s)
+        for (int c = 0; c < 6; ++c) sbf[s * 6 + c] = sd->shells[s].bf[c];
+    if ((e = cudaMalloc((void **)&dev->d_shell_bf, sbf.size() * 4 + 8)) != cudaSuccess) {
+        err = std::string("shell table: ") + cudaGetErrorString(e);
+        return 1;
+    }
+    cudaMemcpyAsync(d_bra_nat, bra.data(), bra.size() * 8, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(dev->d_bra, bra.data(), bra.size() * 8, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(dev->d_ket, ket.data(), ket.size() * 8, cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_meta_nat, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(dev->d_meta, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice, stream);
-    if (!dev->d_shell_bf) {
-        std::vector<int> sbf(sd->shells.size() * 6);
-        for (size_t s = 0; s < sd->shells.size(); ++s)
-            for (int c = 0; c < 6; ++c) sbf[s * 6 + c] = sd->shells[s].bf[c];
-        if ((e = cudaMalloc((void **)&dev->d_shell_bf, sbf.size() * 4 + 8)) != cudaSuccess) {
-            err = std::string("shell table: ") + cudaGetErrorString(e);
-            return 1;
-        }
-        cudaMemcpyAsync(dev->d_shell_bf, sbf.data(), sbf.size() * 4, cudaMemcpyHostToDevice, stream);
-    }
+    cudaMemcpyAsync(dev->d_shell_bf, sbf.data(), sbf.size() * 4, cudaMemcpyHostToDevice, stream);
     e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) {
         err = std::string("pair table upload: ") + cudaGetErrorString(e);
@@ -85,37 +111,32 @@ int ClassEngine::upload_tables(std::string &err) {
     dev->bra_doubles = bra.size();
     dev->ket_doubles = ket.size();
     dev->meta_ints = meta.size();
+    plan_valid = false;
     return 0;
 }
 
-ClassLaunch ClassEngine::base_launch(const Sublist &sb, const Sublist &sk) const {
-    ClassLaunch cl{};
-    cl.bra = dev->d_bra + sb.bra_off;
-    cl.ket = dev->d_ket + sk.ket_off;
-    cl.bra_meta = dev->d_meta + sb.meta_off;
-    cl.ket_meta = dev->d_meta + sk.meta_off;
-    cl.shell_bf = dev->d_shell_bf;
-    cl.boys_lut = boys.lut;
-    cl.boys_tab = boys.tab;
-    cl.Kab = sb.K;
-    cl.Kcd = sk.K;
-    cl.nb = (int)sb.pair_ids.size();
-    cl.nk = (int)sk.pair_ids.size();
-    cl.nk_pad = sk.npad;
-    cl.rank = 0;
-    cl.world = 1;
-    return cl;
-}
-
-// Diagonal pass: every class pair's (AB|AB) block; only (xy|xy) kept.
+// Diagonal pass: every class pair's (AB|AB) block from the natural-order tables; only (xy|xy) kept.
 int ClassEngine::run_diagonal(double *d_diag, std::string &err) {
     int launches = 0;
-    for (const Sublist &s : sd->sublists) {
-        if (s.pair_ids.empty()) continue;
-        ClassLaunch cl = base_launch(s, s);
-        dim3 grid((unsigned)((cl.nb + kClassThreads - 1) / kClassThreads));
-        DiagSink sink{d_diag};
-        launches += launch_class<true>(s.cls, s.cls, cl, sink, mode, grid, stream);
+    const DiagSink sink{d_diag};
+    for (size_t si = 0; si < sd->sublists.size(); ++si) {
+        const Sublist &s = sd->sublists[si];
+        const int n = (int)s.pair_ids.size();
+        if (!n) continue;
+        DiagLaunch dl{d_bra_nat + s.bra_off, d_meta_nat + s.meta_off, dev->d_shell_bf, boys.lut, boys.tab, s.K, n};
+        dim3 grid((unsigned)((n + kClassWarps - 1) / kClassWarps));
+        if (s.cls == 0) {
+            launch_diag_mode<0, 0, 0, 1>(dl, sink, mode, grid, stream);
+            launches += 1;
+        } else if (s.cls == 1) {
+            launch_diag_mode<1, 0, 0, 3>(dl, sink, mode, grid, stream);
+            launches += 1;
+        } else {
+            launch_diag_mode<1, 1, 0, 3>(dl, sink, mode, grid, stream);
+            launch_diag_mode<1, 1, 3, 3>(dl, sink, mode, grid, stream);
+            launch_diag_mode<1, 1, 6, 3>(dl, sink, mode, grid, stream);
+            launches += 3;
+        }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -125,7 +146,8 @@ int ClassEngine::run_diagonal(double *d_diag, std::string &err) {
     return launches;
 }
 
-// After the diagonal is on the host: per-pair max |(xy|xy)|, sort sublists, rebuild tables.
+// With the diagonal on the host: per-pair max |(xy|xy)|, sort each sublist (descending), permute the
+// device tables accordingly.
 int ClassEngine::sort_by_diagonal(const std::vector<double> &h_diag, std::string &err) {
     for (ShellPair &p : sd->pairs) {
         const Shell &A = sd->shells[p.A], &B = sd->shells[p.B];
@@ -135,17 +157,44 @@ int ClassEngine::sort_by_diagonal(const std::vector<double> &h_diag, std::string
                 const int x = A.bf[ca], y = B.bf[cb];
                 if (x < 0 || y < 0) continue;
                 const double d = std::fabs(h_diag[x >= y ? tri(x, y) : tri(y, x)]);
-                if (d > m || std::isnan(d)) m = std::isnan(d) ? INFINITY : d;
+                if (std::isnan(d)) m = INFINITY; else if (d > m) m = d;
             }
         p.maxdiag = m;
     }
-    sort_sublists(*sd);
-    return upload_tables(err);
+    std::vector<int> perm(dev->meta_ints / 2 + 1, 0);
+    int launches = 0;
+    for (size_t si = 0; si < sd->sublists.size(); ++si) {
+        Sublist &s = sd->sublists[si];
+        const std::vector<int> &nat = nat_ids[si];
+        const int n = (int)nat.size();
+        std::vector<int> order(n);
+        std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return sd->pairs[nat[x]].maxdiag > sd->pairs[nat[y]].maxdiag; });
+        for (int i = 0; i < n; ++i) {
+            s.pair_ids[i] = nat[order[i]];
+            perm[s.meta_off / 2 + i] = order[i];
+        }
+    }
+    cudaMemcpyAsync(d_perm, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, stream);
+    for (const Sublist &s : sd->sublists) {
+        const int n = (int)s.pair_ids.size();
+        if (!n) continue;
+        permute_pairs_kernel<<<n, 64, 0, stream>>>(d_bra_nat + s.bra_off, d_meta_nat + s.meta_off, d_perm + s.meta_off / 2, n, s.K, s.nf,
+                                                   s.npad, dev->d_bra + s.bra_off, dev->d_ket + s.ket_off, dev->d_meta + s.meta_off);
+        ++launches;
+    }
+    cudaError_t e = cudaStreamSynchronize(stream);  // `perm` is pageable host memory
+    if (e != cudaSuccess) {
+        err = std::string("permute pair tables: ") + cudaGetErrorString(e);
+        return -1;
+    }
+    plan_valid = false;
+    return launches;
 }
 
-// Number of ket pairs c (sublist sk, sorted descending) that pass the shell-level bound against
-// bra pair value `db`: the basis-function rule sqrt(d1*d2) > thr is monotone in both arguments, so
-// if the bound on the per-pair maxima fails every component fails.
+// Number of ket pairs (sorted descending by maxdiag) that pass the shell-level bound against a bra
+// pair with value db.  The basis-function rule sqrt(d1*d2) > thr is monotone in both arguments, so
+// when the bound on the per-pair maxima fails every component fails.
 static int surviving_prefix(double db, const std::vector<double> &dk, int screen, double thr) {
     if (screen == FOCK_SCREEN_OFF) return (int)dk.size();
     int lo = 0, hi = (int)dk.size();  // first index that fails
@@ -156,59 +205,87 @@ static int surviving_prefix(double db, const std::vector<double> &dk, int screen
     return lo;
 }
 
-int ClassEngine::run_build(const StoreSink &sink, int screen, double thr, int rank, int world, ClassStats &stats,
-                           std::string &err) {
+int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::string &err) {
+    if (plan_valid && plan_screen == screen && plan_thr == thr && plan_rank == rank && plan_world == world) return 0;
     const int ns = (int)sd->sublists.size();
     std::vector<std::vector<double>> md(ns);
     for (int s = 0; s < ns; ++s) {
         md[s].reserve(sd->sublists[s].pair_ids.size());
         for (int id : sd->sublists[s].pair_ids) md[s].push_back(sd->pairs[id].maxdiag);
     }
-    // tile tables for all launches, one upload
-    struct Job {
-        int sb, sk;
-        size_t off;
-        long long tiles;
-    };
-    std::vector<Job> jobs;
     std::vector<int> table;
-    stats = ClassStats();
-    for (int b = 0; b < ns; ++b) {
-        const Sublist &sb = sd->sublists[b];
-        const int nb = (int)sb.pair_ids.size();
-        if (!nb) continue;
-        for (int k = 0; k <= b; ++k) {
-            const Sublist &sk = sd->sublists[k];
-            const int nk = (int)sk.pair_ids.size();
-            if (!nk) continue;
-            Job j{b, k, table.size(), 0};
-            table.resize(table.size() + 2 * (size_t)nb + 1);
-            int *prefix = table.data() + j.off, *ncols = prefix + nb + 1;
-            long long tiles = 0, quartets = 0;
-            for (int r = 0; r < nb; ++r) {
-                int nc = surviving_prefix(md[b][r], md[k], screen, thr);
-                if (b == k) nc = std::min(nc, r + 1);
-                ncols[r] = nc;
-                prefix[r] = (int)tiles;
-                tiles += (nc + kClassThreads - 1) / kClassThreads;
-                quartets += nc;
+    std::vector<ClassJob> jobs;
+    std::vector<size_t> job_table_off;
+    plan.clear();
+    plan_stats = ClassStats();
+    // class pairs in a fixed order; within one, every (bra sublist >= ket sublist) job
+    for (int cb = 0; cb < 3; ++cb)
+        for (int ck = 0; ck <= cb; ++ck) {
+            ClassPlanLaunch pl;
+            pl.cb = cb;
+            pl.ck = ck;
+            pl.job_begin = (int)jobs.size();
+            long long tiles_launch = 0;
+            for (int b = 0; b < ns; ++b) {
+                const Sublist &sb = sd->sublists[b];
+                if (sb.cls != cb || sb.pair_ids.empty()) continue;
+                for (int k = 0; k <= b; ++k) {
+                    const Sublist &sk = sd->sublists[k];
+                    if (sk.cls != ck || sk.pair_ids.empty()) continue;
+                    const int nb = (int)sb.pair_ids.size(), nk = (int)sk.pair_ids.size();
+                    const size_t off = table.size();
+                    table.resize(off + 2 * (size_t)nb + 1);
+                    int *prefix = table.data() + off, *ncols = prefix + nb + 1;
+                    long long tiles = 0, quartets = 0;
+                    for (int r = 0; r < nb; ++r) {
+                        int nc = surviving_prefix(md[b][r], md[k], screen, thr);
+                        if (b == k) nc = std::min(nc, r + 1);
+                        ncols[r] = nc;
+                        prefix[r] = (int)tiles;
+                        tiles += (nc + 31) / 32;
+                        quartets += nc;
+                    }
+                    prefix[nb] = (int)tiles;
+                    if (tiles > 2000000000LL) {
+                        err = "tile table overflow";
+                        return 1;
+                    }
+                    plan_stats.shell_quartets_total += (b == k) ? (long long)nb * (nb + 1) / 2 : (long long)nb * nk;
+                    plan_stats.shell_quartets += quartets;
+                    plan_stats.prim_quartets += quartets * (long long)sb.K * sk.K;
+                    plan_stats.model_flops += (double)quartets * sb.K * sk.K *
+                                              model_flops_per_prim_quartet(kClsLA[cb], kClsLB[cb], kClsLA[ck], kClsLB[ck]);
+                    plan_stats.warp_tiles += tiles;
+                    if (tiles == 0) {
+                        table.resize(off);
+                        continue;
+                    }
+                    ClassJob j{};
+                    j.tile_begin = tiles_launch;
+                    j.bra = dev->d_bra + sb.bra_off;
+                    j.ket = dev->d_ket + sk.ket_off;
+                    j.bra_meta = dev->d_meta + sb.meta_off;
+                    j.ket_meta = dev->d_meta + sk.meta_off;
+                    j.Kab = sb.K;
+                    j.Kcd = sk.K;
+                    j.nb = nb;
+                    j.nk_pad = sk.npad;
+                    j.same_sublist = (b == k) ? 1 : 0;
+                    jobs.push_back(j);
+                    job_table_off.push_back(off);
+                    tiles_launch += tiles;
+                    pl.max_bra_doubles = std::max(pl.max_bra_doubles, sb.K * sb.nf);
+                }
             }
-            prefix[nb] = (int)tiles;
-            if (tiles > 2000000000LL) {
-                err = "tile table overflow";
-                return -1;
+            pl.njobs = (int)jobs.size() - pl.job_begin;
+            pl.total_tiles = tiles_launch;
+            if (pl.njobs > kMaxJobs) {
+                err = "too many sublist pairs in one class launch";
+                return 1;
             }
-            j.tiles = tiles;
-            stats.shell_quartets_total += (b == k) ? (long long)nb * (nb + 1) / 2 : (long long)nb * nk;
-            // work this rank will do: tiles are dealt round-robin, quartet counts are split evenly enough
-            stats.shell_quartets += quartets;
-            stats.prim_quartets += quartets * (long long)sb.K * sk.K;
-            stats.model_flops += (double)quartets * sb.K * sk.K *
-                                 model_flops_per_prim_quartet(kClsLA[sb.cls], kClsLB[sb.cls], kClsLA[sk.cls], kClsLB[sk.cls]);
-            if (tiles > 0) jobs.push_back(j);
+            if (pl.njobs > 0) plan.push_back(pl);
         }
-    }
-    if (table.size() > table_cap) {
+    if (table.size() + 1 > table_cap) {
         if (d_table) cudaFree(d_table);
         d_table = nullptr;
         table_cap = table.size() + table.size() / 4 + 1024;
@@ -216,36 +293,75 @@ int ClassEngine::run_build(const StoreSink &sink, int screen, double thr, int ra
         if (e != cudaSuccess) {
             err = std::string("tile table: ") + cudaGetErrorString(e);
             table_cap = 0;
-            return -1;
+            return 1;
         }
     }
+    if (jobs.size() + 1 > jobs_cap) {
+        if (d_jobs) cudaFree(d_jobs);
+        d_jobs = nullptr;
+        jobs_cap = jobs.size() + 64;
+        cudaError_t e = cudaMalloc((void **)&d_jobs, jobs_cap * sizeof(ClassJob));
+        if (e != cudaSuccess) {
+            err = std::string("job table: ") + cudaGetErrorString(e);
+            jobs_cap = 0;
+            return 1;
+        }
+    }
+    for (size_t i = 0; i < jobs.size(); ++i) {
+        jobs[i].row_prefix = d_table + job_table_off[i];
+        jobs[i].ncols = jobs[i].row_prefix + jobs[i].nb + 1;
+    }
     cudaMemcpyAsync(d_table, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(ClassJob), cudaMemcpyHostToDevice, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);  // pageable sources
+    if (e != cudaSuccess) {
+        err = std::string("plan upload: ") + cudaGetErrorString(e);
+        return 1;
+    }
+    plan_valid = true;
+    plan_screen = screen;
+    plan_thr = thr;
+    plan_rank = rank;
+    plan_world = world;
+    return 0;
+}
+
+template <class Sink>
+int ClassEngine::run_plan(const Sink &sink, std::string &err) {
     int launches = 0;
-    for (const Job &j : jobs) {
-        const Sublist &sb = sd->sublists[j.sb], &sk = sd->sublists[j.sk];
-        ClassLaunch cl = base_launch(sb, sk);
-        cl.tile_prefix = d_table + j.off;
-        cl.ncols = cl.tile_prefix + cl.nb + 1;
-        cl.rank = rank;
-        cl.world = world;
-        cl.total_tiles = j.tiles;
-        const long long mine = (j.tiles - rank + world - 1) / world;
+    for (const ClassPlanLaunch &pl : plan) {
+        ClassLaunch cl{};
+        cl.jobs = d_jobs + pl.job_begin;
+        cl.njobs = pl.njobs;
+        cl.total_tiles = pl.total_tiles;
+        cl.shell_bf = dev->d_shell_bf;
+        cl.boys_lut = boys.lut;
+        cl.boys_tab = boys.tab;
+        cl.rank = plan_rank;
+        cl.world = plan_world;
+        cl.max_bra_doubles = pl.max_bra_doubles;
+        const long long mine = (pl.total_tiles - plan_rank + plan_world - 1) / plan_world;  // warp tiles of this rank
         if (mine <= 0) continue;
-        dim3 grid((unsigned)mine);
-        launches += launch_class<false>(sb.cls, sk.cls, cl, sink, mode, grid, stream);
+        dim3 grid((unsigned)((mine + kClassWarps - 1) / kClassWarps));
+        launches += launch_class(pl.cb, pl.ck, cl, sink, mode, grid, stream);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         err = std::string("class kernels: ") + cudaGetErrorString(e);
         return -1;
     }
-    // the host tile table must stay alive until the copy has been consumed
-    cudaStreamSynchronize(stream);
     return launches;
 }
 
+template int ClassEngine::run_plan<TensorSink>(const TensorSink &, std::string &);
+template int ClassEngine::run_plan<DirectSink>(const DirectSink &, std::string &);
+
 ClassEngine::~ClassEngine() {
     if (d_table) cudaFree(d_table);
+    if (d_jobs) cudaFree(d_jobs);
+    if (d_bra_nat) cudaFree(d_bra_nat);
+    if (d_meta_nat) cudaFree(d_meta_nat);
+    if (d_perm) cudaFree(d_perm);
 }
 
 }  // namespace fock

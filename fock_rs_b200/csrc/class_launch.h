@@ -10,14 +10,24 @@
 
 namespace fock {
 
-struct StoreSink;
-struct ClassLaunch;
+struct TensorSink;
+struct DirectSink;
+struct ClassJob;
 
 struct ClassStats {
     long long shell_quartets_total = 0;  // unique class shell quartets before screening
     long long shell_quartets = 0;        // evaluated (all ranks together)
     long long prim_quartets = 0;
     double model_flops = 0;
+    long long warp_tiles = 0;
+};
+
+// One class-pair launch (all (bra sublist, ket sublist) jobs of one angular class pair).
+struct ClassPlanLaunch {
+    int cb = 0, ck = 0;       // pair classes 0 ss, 1 ps, 2 pp
+    int job_begin = 0, njobs = 0;
+    long long total_tiles = 0;
+    int max_bra_doubles = 0;
 };
 
 struct ClassEngine {
@@ -26,15 +36,30 @@ struct ClassEngine {
     BoysTables boys{};
     cudaStream_t stream = nullptr;
     int mode = 0;
+
+    // natural-order master tables (built once) and the permutation scratch
+    double *d_bra_nat = nullptr;
+    int *d_meta_nat = nullptr;
+    int *d_perm = nullptr;
+    std::vector<std::vector<int>> nat_ids;  // per sublist: pair ids in natural order
+
+    // plan (jobs + tile tables) of the current sorted order / screening
     int *d_table = nullptr;
     size_t table_cap = 0;
+    ClassJob *d_jobs = nullptr;
+    size_t jobs_cap = 0;
+    std::vector<ClassPlanLaunch> plan;
+    ClassStats plan_stats;
+    bool plan_valid = false;
+    int plan_screen = -1, plan_rank = -1, plan_world = -1;
+    double plan_thr = 0;
 
-    int upload_tables(std::string &err);
+    int upload_master(std::string &err);                 // once, after build_pairs
     int run_diagonal(double *d_diag, std::string &err);  // returns launches or -1
-    int sort_by_diagonal(const std::vector<double> &h_diag, std::string &err);
-    int run_build(const StoreSink &sink, int screen, double thr, int rank, int world, ClassStats &stats,
-                  std::string &err);  // returns launches or -1
-    ClassLaunch base_launch(const Sublist &sb, const Sublist &sk) const;
+    int sort_by_diagonal(const std::vector<double> &h_diag, std::string &err);  // returns launches or -1
+    int make_plan(int screen, double thr, int rank, int world, std::string &err);
+    template <class Sink>
+    int run_plan(const Sink &sink, std::string &err);  // returns launches or -1
     ~ClassEngine();
 };
 

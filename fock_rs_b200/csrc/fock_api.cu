@@ -198,7 +198,7 @@ int fock_create(const fock_basis *b, const fock_opts *opts_in, fock_ctx **out) {
         cs->engine.boys = ctx->boys();
         cs->engine.stream = ctx->stream;
         cs->engine.mode = o.mode;
-        if (!ctx->shells.pairs.empty() && cs->engine.upload_tables(err)) {
+        if (!ctx->shells.pairs.empty() && cs->engine.upload_master(err)) {
             ctx->err = err;
             return FOCK_ERR_CUDA;
         }
@@ -274,10 +274,12 @@ static int diagonal_pass(fock_ctx *ctx, int *launches) {
         std::vector<double> h_diag(ctx->npair);
         FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(h_diag.data(), ctx->d_diag, ctx->npair * sizeof(double), cudaMemcpyDeviceToHost, st));
         FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        if (cs->engine.sort_by_diagonal(h_diag, err)) {
+        const int l = cs->engine.sort_by_diagonal(h_diag, err);
+        if (l < 0) {
             ctx->err = err;
             return FOCK_ERR_CUDA;
         }
+        *launches += l;
     }
     return FOCK_OK;
 }
@@ -305,44 +307,54 @@ int fock_eri_build(fock_ctx *ctx) {
     ctx->stats[4] = ctx->stats[5] = 0;
     ctx->stats[8] = 0;
     if (ctx->opts.storage == FOCK_STORAGE_INCORE) {
-        if (!ctx->d_V) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_V, ctx->nelem * sizeof(double)));
-        FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_V, 0, ctx->nelem * sizeof(double), st));
+        // kernel == 1 (forced generic) forms the supermatrix by the gather definition from V; the
+        // default path scatters every integral into P as it is produced (V only if keep_eri).
+        const bool gather = ctx->opts.kernel == 1;
+        const bool want_v = ctx->opts.keep_eri || gather;
+        const size_t chunk = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
+        const size_t padded = chunk * ctx->opts.world;  // equal chunks for the reduce-scatter
+        if (want_v && !ctx->d_V) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_V, ctx->nelem * sizeof(double)));
+        if (!ctx->d_P) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_P, padded * sizeof(double)));
+        if (want_v) FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_V, 0, ctx->nelem * sizeof(double), st));
+        FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_P, 0, padded * sizeof(double), st));
         FOCK_CUDA_TRY(ctx, cudaMemsetAsync(cs->d_counter, 0, sizeof(unsigned long long), st));
         const double thr = screen_threshold(ctx->opts);
+        double *Vp = want_v ? ctx->d_V : nullptr, *Pp = gather ? nullptr : ctx->d_P;
         diag_to_tensor_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(ctx->d_diag, ctx->npair, ctx->opts.rank,
-                                                                                  ctx->opts.world, ctx->d_V);
+                                                                                  ctx->opts.world, Vp, Pp);
         launches += 1;
         if (!ctx->shells.pairs.empty()) {
-            StoreSink sink{ctx->d_V, ctx->d_diag, thr, ctx->opts.screen};
             std::string err;
-            const int l = cs->engine.run_build(sink, ctx->opts.screen, thr, ctx->opts.rank, ctx->opts.world, cs->stats, err);
+            if (cs->engine.make_plan(ctx->opts.screen, thr, ctx->opts.rank, ctx->opts.world, err)) {
+                ctx->err = err;
+                return FOCK_ERR_CUDA;
+            }
+            TensorSink sink{Vp, Pp, ctx->d_diag, thr, ctx->opts.screen};
+            const int l = cs->engine.run_plan(sink, err);
             if (l < 0) {
                 ctx->err = err;
                 return FOCK_ERR_CUDA;
             }
             launches += l;
+            cs->stats = cs->engine.plan_stats;
             ctx->stats[4] = cs->stats.shell_quartets;
             ctx->stats[5] = cs->stats.prim_quartets;
             ctx->stats[8] = (int64_t)cs->stats.model_flops;
+            ctx->stats[10] = cs->stats.warp_tiles;
         }
         if (!ctx->shells.all_class_ok) {
             const size_t mine = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
             generic_tensor_kernel<<<(unsigned)((mine + T - 1) / T), T, 0, st>>>(
                 ctx->basis_dev(), ctx->boys(), ctx->opts.mode, cs->d_bf_class_ok, 1, ctx->opts.screen, thr, ctx->d_diag,
-                ctx->nelem, ctx->opts.rank, ctx->opts.world, ctx->d_V, cs->d_counter);
+                ctx->nelem, ctx->opts.rank, ctx->opts.world, Vp, Pp, cs->d_counter);
             launches += 1;
         }
         FOCK_CUDA_TRY(ctx, cudaGetLastError());
         FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_C], st));
-        const size_t chunk = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
-        const size_t padded = chunk * ctx->opts.world;  // equal chunks for the reduce-scatter
-        if (!ctx->d_P) {
-            FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_P, padded * sizeof(double)));
-            if (padded > ctx->nelem)
-                FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_P + ctx->nelem, 0, (padded - ctx->nelem) * sizeof(double), st));
+        if (gather) {
+            supermatrix_kernel<<<(unsigned)((ctx->nelem + 255) / 256), 256, 0, st>>>(ctx->d_V, ctx->d_P, ctx->nelem);
+            launches += 1;
         }
-        supermatrix_kernel<<<(unsigned)((ctx->nelem + 255) / 256), 256, 0, st>>>(ctx->d_V, ctx->d_P, ctx->nelem);
-        launches += 1;
         FOCK_CUDA_TRY(ctx, cudaGetLastError());
         FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_D], st));
         unsigned long long generic_eval = 0;
@@ -356,10 +368,6 @@ int fock_eri_build(fock_ctx *ctx) {
         ctx->timings[1] = ms;
         cudaEventElapsedTime(&ms, ctx->ev[EV_C], ctx->ev[EV_D]);
         ctx->timings[2] = ms;
-        if (!ctx->opts.keep_eri) {
-            cudaFree(ctx->d_V);
-            ctx->d_V = nullptr;
-        }
     } else {
         FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
         float ms = 0;
@@ -492,8 +500,41 @@ int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev) {
         unpack_result_kernel<<<(unsigned)(((size_t)ctx->N * ctx->N + 255) / 256), 256, 0, st>>>(ctx->d_yvec, ctx->N, G_dev);
         launches += 2;
     } else {
-        ctx->err = "integral-direct G build is not available in this build";
-        return FOCK_ERR_UNSUPPORTED;
+        // integral-direct: regenerate every surviving integral and digest it on the fly
+        ClassState *cs = cls(ctx);
+        const double thr = screen_threshold(ctx->opts);
+        pack_density_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(D_dev, ctx->N, ctx->d_dvec, ctx->d_yvec, ctx->npair);
+        diag_digest_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(ctx->d_diag, ctx->npair, ctx->opts.rank, ctx->opts.world,
+                                                                               ctx->d_dvec, ctx->d_yvec);
+        launches += 2;
+        if (!ctx->shells.pairs.empty()) {
+            std::string err;
+            if (cs->engine.make_plan(ctx->opts.screen, thr, ctx->opts.rank, ctx->opts.world, err)) {
+                ctx->err = err;
+                return FOCK_ERR_CUDA;
+            }
+            DirectSink sink{ctx->d_yvec, ctx->d_dvec, ctx->d_diag, thr, ctx->opts.screen};
+            const int l = cs->engine.run_plan(sink, err);
+            if (l < 0) {
+                ctx->err = err;
+                return FOCK_ERR_CUDA;
+            }
+            launches += l;
+            cs->stats = cs->engine.plan_stats;
+            ctx->stats[4] = cs->stats.shell_quartets;
+            ctx->stats[5] = cs->stats.prim_quartets;
+            ctx->stats[8] = (int64_t)cs->stats.model_flops;
+            ctx->stats[10] = cs->stats.warp_tiles;
+        }
+        if (!ctx->shells.all_class_ok) {
+            const size_t mine = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
+            generic_direct_kernel<<<(unsigned)((mine + 127) / 128), 128, 0, st>>>(
+                ctx->basis_dev(), ctx->boys(), ctx->opts.mode, cs->d_bf_class_ok, 1, ctx->opts.screen, thr, ctx->d_diag, ctx->nelem,
+                ctx->opts.rank, ctx->opts.world, ctx->d_dvec, ctx->d_yvec);
+            launches += 1;
+        }
+        unpack_result_kernel<<<(unsigned)(((size_t)ctx->N * ctx->N + 255) / 256), 256, 0, st>>>(ctx->d_yvec, ctx->N, G_dev);
+        launches += 1;
     }
     FOCK_CUDA_TRY(ctx, cudaGetLastError());
     FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_F], st));

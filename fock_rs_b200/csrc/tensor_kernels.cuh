@@ -4,6 +4,7 @@
 #pragma once
 #include "device_math.cuh"
 #include "eri_generic.cuh"
+#include "super_scatter.cuh"
 
 namespace fock {
 
@@ -24,7 +25,7 @@ __global__ void generic_diag_kernel(BasisDev bs, BoysTables bt, int mode, const 
 // kernels do not cover, with the reference's screening rule (electron_tensor.rs:129-158).
 __global__ void generic_tensor_kernel(BasisDev bs, BoysTables bt, int mode, const unsigned char *bf_class_ok,
                                       int skip_class, int screen, double thr, const double *diag, size_t nelem,
-                                      int rank, int world, double *V, unsigned long long *n_eval) {
+                                      int rank, int world, double *V, double *P, unsigned long long *n_eval) {
     const size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * (size_t)world + (size_t)rank;
     if (e >= nelem) return;
     size_t xy, zw, x, y, z, w;
@@ -33,24 +34,54 @@ __global__ void generic_tensor_kernel(BasisDev bs, BoysTables bt, int mode, cons
     untri(zw, z, w);
     if (xy == zw) return;  // diagonal slots: diag_to_tensor_kernel
     if (skip_class && bf_class_ok[x] && bf_class_ok[y] && bf_class_ok[z] && bf_class_ok[w]) return;
-    double v = 0.0;
-    bool keep = true;
-    if (screen != 1) keep = sqrt(diag[xy] * diag[zw]) > thr;
-    if (keep) {
-        v = eri_function_quartet(bs, (int)x, (int)y, (int)z, (int)w, mode, bt);
-        atomicAdd(n_eval, 1ULL);
-    }
-    V[e] = v;
+    if (screen != 1 && !(sqrt(diag[xy] * diag[zw]) > thr)) return;  // slot stays 0.0
+    const double v = eri_function_quartet(bs, (int)x, (int)y, (int)z, (int)w, mode, bt);
+    atomicAdd(n_eval, 1ULL);
+    if (V) V[e] = v;
+    if (P) scatter_super(P, (int)x, (int)y, (int)z, (int)w, v);
+}
+
+// ---- integral-direct remainder: the same loop digesting into y instead of storing
+__global__ void generic_direct_kernel(BasisDev bs, BoysTables bt, int mode, const unsigned char *bf_class_ok,
+                                      int skip_class, int screen, double thr, const double *diag, size_t nelem,
+                                      int rank, int world, const double *d, double *y) {
+    const size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * (size_t)world + (size_t)rank;
+    if (e >= nelem) return;
+    size_t xy, zw, x, y_, z, w;
+    untri(e, xy, zw);
+    untri(xy, x, y_);
+    untri(zw, z, w);
+    if (xy == zw) return;
+    if (skip_class && bf_class_ok[x] && bf_class_ok[y_] && bf_class_ok[z] && bf_class_ok[w]) return;
+    if (screen != 1 && !(sqrt(diag[xy] * diag[zw]) > thr)) return;
+    const double v = eri_function_quartet(bs, (int)x, (int)y_, (int)z, (int)w, mode, bt);
+    digest_super(y, d, (int)x, (int)y_, (int)z, (int)w, v);
 }
 
 // ---- the diagonal pass's results go into the tensor unconditionally (the reference computes
 // (ij|ij) before and outside the screened loop, electron_tensor.rs:90-101).  With several ranks each
 // diagonal slot is written by exactly one of them so that partial tensors sum correctly.
 __global__ void diag_to_tensor_kernel(const double *__restrict__ diag, size_t npair, int rank, int world,
-                                      double *__restrict__ V) {
+                                      double *__restrict__ V, double *__restrict__ P) {
     const size_t xy = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (xy >= npair || (int)(xy % (size_t)world) != rank) return;
-    V[tri(xy, xy)] = diag[xy];
+    const double v = diag[xy];
+    if (V) V[tri(xy, xy)] = v;
+    if (P) {
+        size_t x, y;
+        untri(xy, x, y);
+        scatter_super(P, (int)x, (int)y, (int)x, (int)y, v);
+    }
+}
+
+// integral-direct: the diagonal integrals digested from the stored diagonal
+__global__ void diag_digest_kernel(const double *__restrict__ diag, size_t npair, int rank, int world,
+                                   const double *__restrict__ d, double *__restrict__ y) {
+    const size_t xy = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (xy >= npair || (int)(xy % (size_t)world) != rank) return;
+    size_t x, yy;
+    untri(xy, x, yy);
+    digest_super(y, d, (int)x, (int)yy, (int)x, (int)yy, diag[xy]);
 }
 
 // ---- batch of arbitrary function quartets (fock_eri_batch)
