@@ -29,7 +29,7 @@ void launch_mode(const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, s
 
 template <class Sink>
 int launch_class(int cb, int ck, const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, cudaStream_t st) {
-    const size_t smem = (size_t)cl.max_bra_doubles * kClassWarps * sizeof(double);
+    const size_t smem = 0;
     switch (cb * 3 + ck) {
         case 0: launch_mode<0, 0, 0, 0, 0, 1>(cl, sink, mode, grid, smem, st); return 1;
         case 3: launch_mode<1, 0, 0, 0, 0, 1>(cl, sink, mode, grid, smem, st); return 1;
@@ -86,7 +86,8 @@ int ClassEngine::upload_master(std::string &err) {
     auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 8); };
     if ((e = alloc((void **)&d_bra_nat, bra.size() * 8)) != cudaSuccess || (e = alloc((void **)&dev->d_bra, bra.size() * 8)) != cudaSuccess ||
         (e = alloc((void **)&dev->d_ket, ket.size() * 8)) != cudaSuccess || (e = alloc((void **)&d_meta_nat, meta.size() * 4)) != cudaSuccess ||
-        (e = alloc((void **)&dev->d_meta, meta.size() * 4)) != cudaSuccess || (e = alloc((void **)&d_perm, meta.size() * 2 + 8)) != cudaSuccess) {
+        (e = alloc((void **)&dev->d_meta, meta.size() * 4)) != cudaSuccess || (e = alloc((void **)&d_perm, meta.size() * 2 + 8)) != cudaSuccess ||
+        (e = cudaMallocHost((void **)&h_perm, meta.size() * 2 + 8)) != cudaSuccess) {
         err = std::string("pair tables: ") + cudaGetErrorString(e);
         return 1;
     }
@@ -161,7 +162,7 @@ int ClassEngine::sort_by_diagonal(const std::vector<double> &h_diag, std::string
             }
         p.maxdiag = m;
     }
-    std::vector<int> perm(dev->meta_ints / 2 + 1, 0);
+    int *perm = h_perm;  // pinned; one entry per class pair
     int launches = 0;
     for (size_t si = 0; si < sd->sublists.size(); ++si) {
         Sublist &s = sd->sublists[si];
@@ -175,7 +176,7 @@ int ClassEngine::sort_by_diagonal(const std::vector<double> &h_diag, std::string
             perm[s.meta_off / 2 + i] = order[i];
         }
     }
-    cudaMemcpyAsync(d_perm, perm.data(), perm.size() * sizeof(int), cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_perm, perm, (dev->meta_ints / 2) * sizeof(int), cudaMemcpyHostToDevice, stream);
     for (const Sublist &s : sd->sublists) {
         const int n = (int)s.pair_ids.size();
         if (!n) continue;
@@ -183,7 +184,7 @@ int ClassEngine::sort_by_diagonal(const std::vector<double> &h_diag, std::string
                                                    s.npad, dev->d_bra + s.bra_off, dev->d_ket + s.ket_off, dev->d_meta + s.meta_off);
         ++launches;
     }
-    cudaError_t e = cudaStreamSynchronize(stream);  // `perm` is pageable host memory
+    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         err = std::string("permute pair tables: ") + cudaGetErrorString(e);
         return -1;
@@ -213,7 +214,7 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
         md[s].reserve(sd->sublists[s].pair_ids.size());
         for (int id : sd->sublists[s].pair_ids) md[s].push_back(sd->pairs[id].maxdiag);
     }
-    std::vector<int> table;
+    std::vector<long long> table;
     std::vector<ClassJob> jobs;
     std::vector<size_t> job_table_off;
     plan.clear();
@@ -234,22 +235,19 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
                     if (sk.cls != ck || sk.pair_ids.empty()) continue;
                     const int nb = (int)sb.pair_ids.size(), nk = (int)sk.pair_ids.size();
                     const size_t off = table.size();
-                    table.resize(off + 2 * (size_t)nb + 1);
-                    int *prefix = table.data() + off, *ncols = prefix + nb + 1;
-                    long long tiles = 0, quartets = 0;
+                    table.resize(off + (size_t)nb + 1);
+                    long long *prefix = table.data() + off;
+                    long long quartets = 0;
+                    // ncols(r) is non-increasing in r (both lists sorted descending): walk it down
+                    int nc = (screen == FOCK_SCREEN_OFF) ? nk : surviving_prefix(md[b][0], md[k], screen, thr);
                     for (int r = 0; r < nb; ++r) {
-                        int nc = surviving_prefix(md[b][r], md[k], screen, thr);
-                        if (b == k) nc = std::min(nc, r + 1);
-                        ncols[r] = nc;
-                        prefix[r] = (int)tiles;
-                        tiles += (nc + 31) / 32;
-                        quartets += nc;
+                        if (screen != FOCK_SCREEN_OFF)
+                            while (nc > 0 && !(std::sqrt(md[b][r] * md[k][nc - 1]) > thr)) --nc;
+                        prefix[r] = quartets;
+                        quartets += (b == k) ? std::min(nc, r + 1) : nc;
                     }
-                    prefix[nb] = (int)tiles;
-                    if (tiles > 2000000000LL) {
-                        err = "tile table overflow";
-                        return 1;
-                    }
+                    prefix[nb] = quartets;
+                    const long long tiles = (quartets + 31) / 32;
                     plan_stats.shell_quartets_total += (b == k) ? (long long)nb * (nb + 1) / 2 : (long long)nb * nk;
                     plan_stats.shell_quartets += quartets;
                     plan_stats.prim_quartets += quartets * (long long)sb.K * sk.K;
@@ -274,7 +272,6 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
                     jobs.push_back(j);
                     job_table_off.push_back(off);
                     tiles_launch += tiles;
-                    pl.max_bra_doubles = std::max(pl.max_bra_doubles, sb.K * sb.nf);
                 }
             }
             pl.njobs = (int)jobs.size() - pl.job_begin;
@@ -285,12 +282,15 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
             }
             if (pl.njobs > 0) plan.push_back(pl);
         }
+    cudaError_t e;
     if (table.size() + 1 > table_cap) {
         if (d_table) cudaFree(d_table);
+        if (h_table) cudaFreeHost(h_table);
         d_table = nullptr;
+        h_table = nullptr;
         table_cap = table.size() + table.size() / 4 + 1024;
-        cudaError_t e = cudaMalloc((void **)&d_table, table_cap * sizeof(int));
-        if (e != cudaSuccess) {
+        if ((e = cudaMalloc((void **)&d_table, table_cap * sizeof(long long))) != cudaSuccess ||
+            (e = cudaMallocHost((void **)&h_table, table_cap * sizeof(long long))) != cudaSuccess) {
             err = std::string("tile table: ") + cudaGetErrorString(e);
             table_cap = 0;
             return 1;
@@ -298,22 +298,24 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
     }
     if (jobs.size() + 1 > jobs_cap) {
         if (d_jobs) cudaFree(d_jobs);
+        if (h_jobs) cudaFreeHost(h_jobs);
         d_jobs = nullptr;
+        h_jobs = nullptr;
         jobs_cap = jobs.size() + 64;
-        cudaError_t e = cudaMalloc((void **)&d_jobs, jobs_cap * sizeof(ClassJob));
-        if (e != cudaSuccess) {
+        if ((e = cudaMalloc((void **)&d_jobs, jobs_cap * sizeof(ClassJob))) != cudaSuccess ||
+            (e = cudaMallocHost((void **)&h_jobs, jobs_cap * sizeof(ClassJob))) != cudaSuccess) {
             err = std::string("job table: ") + cudaGetErrorString(e);
             jobs_cap = 0;
             return 1;
         }
     }
-    for (size_t i = 0; i < jobs.size(); ++i) {
-        jobs[i].row_prefix = d_table + job_table_off[i];
-        jobs[i].ncols = jobs[i].row_prefix + jobs[i].nb + 1;
-    }
-    cudaMemcpyAsync(d_table, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice, stream);
-    cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(ClassJob), cudaMemcpyHostToDevice, stream);
-    cudaError_t e = cudaStreamSynchronize(stream);  // pageable sources
+    for (size_t i = 0; i < jobs.size(); ++i) jobs[i].row_prefix = d_table + job_table_off[i];
+    // pinned staging: the copies are truly asynchronous and ordered before the launches on `stream`
+    std::copy(table.begin(), table.end(), h_table);
+    std::copy(jobs.begin(), jobs.end(), h_jobs);
+    cudaMemcpyAsync(d_table, h_table, table.size() * sizeof(long long), cudaMemcpyHostToDevice, stream);
+    cudaMemcpyAsync(d_jobs, h_jobs, jobs.size() * sizeof(ClassJob), cudaMemcpyHostToDevice, stream);
+    e = cudaGetLastError();
     if (e != cudaSuccess) {
         err = std::string("plan upload: ") + cudaGetErrorString(e);
         return 1;
@@ -339,7 +341,6 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
         cl.boys_tab = boys.tab;
         cl.rank = plan_rank;
         cl.world = plan_world;
-        cl.max_bra_doubles = pl.max_bra_doubles;
         const long long mine = (pl.total_tiles - plan_rank + plan_world - 1) / plan_world;  // warp tiles of this rank
         if (mine <= 0) continue;
         dim3 grid((unsigned)((mine + kClassWarps - 1) / kClassWarps));
@@ -362,6 +363,9 @@ ClassEngine::~ClassEngine() {
     if (d_bra_nat) cudaFree(d_bra_nat);
     if (d_meta_nat) cudaFree(d_meta_nat);
     if (d_perm) cudaFree(d_perm);
+    if (h_perm) cudaFreeHost(h_perm);
+    if (h_table) cudaFreeHost(h_table);
+    if (h_jobs) cudaFreeHost(h_jobs);
 }
 
 }  // namespace fock

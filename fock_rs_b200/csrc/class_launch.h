@@ -27,7 +27,6 @@ struct ClassPlanLaunch {
     int cb = 0, ck = 0;       // pair classes 0 ss, 1 ps, 2 pp
     int job_begin = 0, njobs = 0;
     long long total_tiles = 0;
-    int max_bra_doubles = 0;
 };
 
 struct ClassEngine {
@@ -44,8 +43,13 @@ struct ClassEngine {
     std::vector<std::vector<int>> nat_ids;  // per sublist: pair ids in natural order
 
     // plan (jobs + tile tables) of the current sorted order / screening
-    int *d_table = nullptr;
+    long long *d_table = nullptr;
     size_t table_cap = 0;
+    long long *h_table = nullptr;  // pinned staging
+    size_t h_table_cap = 0;
+    ClassJob *h_jobs = nullptr;    // pinned staging
+    int *h_perm = nullptr;         // pinned staging
+    double host_ms[4] = {0, 0, 0, 0};  // sort, plan
     ClassJob *d_jobs = nullptr;
     size_t jobs_cap = 0;
     std::vector<ClassPlanLaunch> plan;

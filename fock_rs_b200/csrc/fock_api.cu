@@ -1,4 +1,5 @@
 // fock_api.cu -- implementation of the C ABI in include/fock_b200.h.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -42,6 +43,8 @@ struct ClassState {
     ClassStats stats;
     unsigned char *d_bf_class_ok = nullptr;
     unsigned long long *d_counter = nullptr;
+    double *h_diag = nullptr;  // pinned image of d_diag
+    cudaEvent_t ev_diag = nullptr;
 };
 
 ClassState *cls(fock_ctx *ctx);
@@ -236,6 +239,8 @@ void fock_destroy(fock_ctx *c) {
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->cs.h_diag) cudaFreeHost(ctx->cs.h_diag);
+    if (ctx->cs.ev_diag) cudaEventDestroy(ctx->cs.ev_diag);
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -249,12 +254,17 @@ int fock_set_stream(fock_ctx *ctx, void *s) {
     return FOCK_OK;
 }
 
-// Diagonal pass shared by both storage modes: fills d_diag and orders the class sublists.
-static int diagonal_pass(fock_ctx *ctx, int *launches) {
+// Diagonal pass shared by both storage modes, in two halves so that independent device work (the
+// tensor memsets) can be queued between them and overlap the host-side sorting:
+//   diagonal_launch : kernels filling d_diag + asynchronous copy to the pinned host image
+//   diagonal_finish : wait for that copy, order the class sublists by their largest diagonal
+static int diagonal_launch(fock_ctx *ctx, int *launches) {
     ClassState *cs = cls(ctx);
     cudaStream_t st = ctx->stream;
     const int T = 128;
     std::string err;
+    if (!cs->h_diag) FOCK_CUDA_TRY(ctx, cudaMallocHost((void **)&cs->h_diag, ctx->npair * sizeof(double)));
+    if (!cs->ev_diag) FOCK_CUDA_TRY(ctx, cudaEventCreateWithFlags(&cs->ev_diag, cudaEventDisableTiming));
     FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_diag, 0, ctx->npair * sizeof(double), st));
     if (!ctx->shells.pairs.empty()) {
         const int l = cs->engine.run_diagonal(ctx->d_diag, err);
@@ -270,17 +280,38 @@ static int diagonal_pass(fock_ctx *ctx, int *launches) {
         *launches += 1;
     }
     FOCK_CUDA_TRY(ctx, cudaGetLastError());
+    FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(cs->h_diag, ctx->d_diag, ctx->npair * sizeof(double), cudaMemcpyDeviceToHost, st));
+    FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_diag, st));
+    return FOCK_OK;
+}
+
+static int diagonal_finish(fock_ctx *ctx, int *launches) {
+    ClassState *cs = cls(ctx);
+    FOCK_CUDA_TRY(ctx, cudaEventSynchronize(cs->ev_diag));
     if (!ctx->shells.pairs.empty()) {
-        std::vector<double> h_diag(ctx->npair);
-        FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(h_diag.data(), ctx->d_diag, ctx->npair * sizeof(double), cudaMemcpyDeviceToHost, st));
-        FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-        const int l = cs->engine.sort_by_diagonal(h_diag, err);
+        const auto t0 = std::chrono::steady_clock::now();
+        std::string err;
+        std::vector<double> h(cs->h_diag, cs->h_diag + ctx->npair);
+        const int l = cs->engine.sort_by_diagonal(h, err);
         if (l < 0) {
             ctx->err = err;
             return FOCK_ERR_CUDA;
         }
         *launches += l;
+        ctx->timings[5] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
+    return FOCK_OK;
+}
+
+static int make_plan_timed(fock_ctx *ctx, double thr) {
+    ClassState *cs = cls(ctx);
+    const auto t0 = std::chrono::steady_clock::now();
+    std::string err;
+    if (cs->engine.make_plan(ctx->opts.screen, thr, ctx->opts.rank, ctx->opts.world, err)) {
+        ctx->err = err;
+        return FOCK_ERR_CUDA;
+    }
+    ctx->timings[6] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return FOCK_OK;
 }
 
@@ -302,7 +333,7 @@ int fock_eri_build(fock_ctx *ctx) {
     int launches = 0;
     const int T = 128;
     FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_A], st));
-    FOCK_TRY(diagonal_pass(ctx, &launches));
+    FOCK_TRY(diagonal_launch(ctx, &launches));
     FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_B], st));
     ctx->stats[4] = ctx->stats[5] = 0;
     ctx->stats[8] = 0;
@@ -318,6 +349,7 @@ int fock_eri_build(fock_ctx *ctx) {
         if (want_v) FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_V, 0, ctx->nelem * sizeof(double), st));
         FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_P, 0, padded * sizeof(double), st));
         FOCK_CUDA_TRY(ctx, cudaMemsetAsync(cs->d_counter, 0, sizeof(unsigned long long), st));
+        FOCK_TRY(diagonal_finish(ctx, &launches));  // host sorting overlaps the memsets above
         const double thr = screen_threshold(ctx->opts);
         double *Vp = want_v ? ctx->d_V : nullptr, *Pp = gather ? nullptr : ctx->d_P;
         diag_to_tensor_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(ctx->d_diag, ctx->npair, ctx->opts.rank,
@@ -325,10 +357,7 @@ int fock_eri_build(fock_ctx *ctx) {
         launches += 1;
         if (!ctx->shells.pairs.empty()) {
             std::string err;
-            if (cs->engine.make_plan(ctx->opts.screen, thr, ctx->opts.rank, ctx->opts.world, err)) {
-                ctx->err = err;
-                return FOCK_ERR_CUDA;
-            }
+            FOCK_TRY(make_plan_timed(ctx, thr));
             TensorSink sink{Vp, Pp, ctx->d_diag, thr, ctx->opts.screen};
             const int l = cs->engine.run_plan(sink, err);
             if (l < 0) {
@@ -369,6 +398,7 @@ int fock_eri_build(fock_ctx *ctx) {
         cudaEventElapsedTime(&ms, ctx->ev[EV_C], ctx->ev[EV_D]);
         ctx->timings[2] = ms;
     } else {
+        FOCK_TRY(diagonal_finish(ctx, &launches));
         FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev[EV_A], ctx->ev[EV_B]);
@@ -509,10 +539,7 @@ int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev) {
         launches += 2;
         if (!ctx->shells.pairs.empty()) {
             std::string err;
-            if (cs->engine.make_plan(ctx->opts.screen, thr, ctx->opts.rank, ctx->opts.world, err)) {
-                ctx->err = err;
-                return FOCK_ERR_CUDA;
-            }
+            FOCK_TRY(make_plan_timed(ctx, thr));
             DirectSink sink{ctx->d_yvec, ctx->d_dvec, ctx->d_diag, thr, ctx->opts.screen};
             const int l = cs->engine.run_plan(sink, err);
             if (l < 0) {

@@ -11,7 +11,7 @@ namespace fock {
 
 int pair_fields(int cls) {
     switch (cls) {
-        case 0: return 5;   // p Px Py Pz K
+        case 0: return 6;   // p Px Py Pz K (pad)
         case 1: return 8;   // p Px Py Pz KWx KWy KWz Kh
         default: return 20; // p Px Py Pz KAB[3][3] KhA[3] KhB[3] Khh
     }
@@ -153,6 +153,7 @@ static void fill_record(const ShellData &sd, const ShellPair &pr, int i, int j, 
     for (int k = 0; k < 3; ++k) rec[1 + k] = (a * A.c[k] + b * B.c[k]) / p;
     if (pr.cls == 0) {
         rec[4] = K;
+        rec[5] = 0.0;
         return;
     }
     const double h = 1.0 / (2.0 * p);

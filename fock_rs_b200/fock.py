@@ -146,7 +146,8 @@ class FockBuilder:
     def timings(self) -> dict:
         ms = (C.c_double * 8)()
         self._check(self._L.fock_timings(self._ctx, ms, 8))
-        return {"diag_ms": ms[0], "eri_ms": ms[1], "supermatrix_ms": ms[2], "g_device_ms": ms[3], "g_e2e_ms": ms[4]}
+        return {"diag_ms": ms[0], "eri_ms": ms[1], "supermatrix_ms": ms[2], "g_device_ms": ms[3], "g_e2e_ms": ms[4],
+                "host_sort_ms": ms[5], "host_plan_ms": ms[6]}
 
     def stats(self) -> dict:
         s = (C.c_int64 * 16)()
@@ -154,7 +155,7 @@ class FockBuilder:
         return {
             "n_basis": s[0], "shells": s[1], "shell_pairs": s[2], "shell_quartets_unique": s[3],
             "shell_quartets_evaluated": s[4], "prim_quartets_evaluated": s[5], "launches_build": s[6],
-            "launches_g": s[7], "model_flops": s[8], "generic_integrals_evaluated": s[9],
+            "launches_g": s[7], "model_flops": s[8], "generic_integrals_evaluated": s[9], "warp_tiles": s[10],
         }
 
 
