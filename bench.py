@@ -272,16 +272,12 @@ def run_ours(args):
 
     def step_device():
         b.eri_build()
-        if world > 1 and storage == _lib.STORAGE_INCORE:
-            parallel.reduce_scatter_supermatrix(b, rank, world)
         b.build_g_device(D.data_ptr(), G.data_ptr())
         if world > 1:
             parallel.allreduce_device(G)
 
     def step_host():
         b.eri_build()
-        if world > 1 and storage == _lib.STORAGE_INCORE:
-            parallel.reduce_scatter_supermatrix(b, rank, world)
         g = b.build_g(Dh)
         if world > 1:
             g = parallel.allreduce_host_matrix(g)

@@ -303,11 +303,11 @@ static int diagonal_finish(fock_ctx *ctx, int *launches) {
     return FOCK_OK;
 }
 
-static int make_plan_timed(fock_ctx *ctx, double thr) {
+static int make_plan_timed(fock_ctx *ctx, double thr, int rank, int world) {
     ClassState *cs = cls(ctx);
     const auto t0 = std::chrono::steady_clock::now();
     std::string err;
-    if (cs->engine.make_plan(ctx->opts.screen, thr, ctx->opts.rank, ctx->opts.world, err)) {
+    if (cs->engine.make_plan(ctx->opts.screen, thr, rank, world, err)) {
         ctx->err = err;
         return FOCK_ERR_CUDA;
     }
@@ -342,8 +342,7 @@ int fock_eri_build(fock_ctx *ctx) {
         // default path scatters every integral into P as it is produced (V only if keep_eri).
         const bool gather = ctx->opts.kernel == 1;
         const bool want_v = ctx->opts.keep_eri || gather;
-        const size_t chunk = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
-        const size_t padded = chunk * ctx->opts.world;  // equal chunks for the reduce-scatter
+        const size_t padded = ctx->nelem;
         if (want_v && !ctx->d_V) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_V, ctx->nelem * sizeof(double)));
         if (!ctx->d_P) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_P, padded * sizeof(double)));
         if (want_v) FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_V, 0, ctx->nelem * sizeof(double), st));
@@ -352,12 +351,16 @@ int fock_eri_build(fock_ctx *ctx) {
         FOCK_TRY(diagonal_finish(ctx, &launches));  // host sorting overlaps the memsets above
         const double thr = screen_threshold(ctx->opts);
         double *Vp = want_v ? ctx->d_V : nullptr, *Pp = gather ? nullptr : ctx->d_P;
-        diag_to_tensor_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(ctx->d_diag, ctx->npair, ctx->opts.rank,
-                                                                                  ctx->opts.world, Vp, Pp);
+        // In-core builds are REPLICATED across ranks (every rank forms the whole supermatrix, ~ms);
+        // what is sharded is the per-iteration streaming of it (fock_set_digest_range).  Sharding the
+        // build instead would need a reduce-scatter of the full packed tensor (1.9 GB at N=208, more
+        // than the build itself costs).  The integral-direct path shards the quartet tiles.
+        const int b_rank = 0, b_world = 1;
+        diag_to_tensor_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(ctx->d_diag, ctx->npair, b_rank, b_world, Vp, Pp);
         launches += 1;
         if (!ctx->shells.pairs.empty()) {
             std::string err;
-            FOCK_TRY(make_plan_timed(ctx, thr));
+            FOCK_TRY(make_plan_timed(ctx, thr, b_rank, b_world));
             TensorSink sink{Vp, Pp, ctx->d_diag, thr, ctx->opts.screen};
             const int l = cs->engine.run_plan(sink, err);
             if (l < 0) {
@@ -372,10 +375,9 @@ int fock_eri_build(fock_ctx *ctx) {
             ctx->stats[10] = cs->stats.warp_tiles;
         }
         if (!ctx->shells.all_class_ok) {
-            const size_t mine = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
-            generic_tensor_kernel<<<(unsigned)((mine + T - 1) / T), T, 0, st>>>(
+            generic_tensor_kernel<<<(unsigned)((ctx->nelem + T - 1) / T), T, 0, st>>>(
                 ctx->basis_dev(), ctx->boys(), ctx->opts.mode, cs->d_bf_class_ok, 1, ctx->opts.screen, thr, ctx->d_diag,
-                ctx->nelem, ctx->opts.rank, ctx->opts.world, Vp, Pp, cs->d_counter);
+                ctx->nelem, b_rank, b_world, Vp, Pp, cs->d_counter);
             launches += 1;
         }
         FOCK_CUDA_TRY(ctx, cudaGetLastError());
@@ -404,6 +406,12 @@ int fock_eri_build(fock_ctx *ctx) {
         cudaEventElapsedTime(&ms, ctx->ev[EV_A], ctx->ev[EV_B]);
         ctx->timings[0] = ms;
         ctx->timings[1] = ctx->timings[2] = 0;
+    }
+    if (ctx->opts.storage == FOCK_STORAGE_INCORE && ctx->opts.world > 1) {
+        // default sharding of the digestion: equal contiguous element ranges of the packed supermatrix
+        const size_t chunk = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
+        ctx->digest_begin = std::min(ctx->nelem, chunk * (size_t)ctx->opts.rank);
+        ctx->digest_end = std::min(ctx->nelem, chunk * ((size_t)ctx->opts.rank + 1));
     }
     ctx->stats[6] = launches;
     ctx->built = true;
@@ -539,7 +547,7 @@ int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev) {
         launches += 2;
         if (!ctx->shells.pairs.empty()) {
             std::string err;
-            FOCK_TRY(make_plan_timed(ctx, thr));
+            FOCK_TRY(make_plan_timed(ctx, thr, ctx->opts.rank, ctx->opts.world));
             DirectSink sink{ctx->d_yvec, ctx->d_dvec, ctx->d_diag, thr, ctx->opts.screen};
             const int l = cs->engine.run_plan(sink, err);
             if (l < 0) {
@@ -637,8 +645,7 @@ int fock_supermatrix_device(fock_ctx *ctx, void **dev_ptr, size_t *n_elements) {
         return FOCK_ERR_STATE;
     }
     *dev_ptr = ctx->d_P;
-    const size_t chunk = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
-    *n_elements = chunk * ctx->opts.world;  // padded length (>= fock_packed_len(N))
+    *n_elements = ctx->nelem;
     return FOCK_OK;
 }
 

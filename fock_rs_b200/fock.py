@@ -218,10 +218,6 @@ class FockEngine:
     def from_basis(self, flat):
         b = self._ensure(flat)
         b.eri_build()
-        if self.distributed and self.world > 1 and self.kw["storage"] == _lib.STORAGE_INCORE:
-            from .parallel import reduce_scatter_supermatrix
-
-            reduce_scatter_supermatrix(b, self.rank, self.world)
 
     def build_g(self, D):
         G = self.builder.build_g(D)

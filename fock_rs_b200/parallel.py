@@ -3,8 +3,8 @@
 The path shards naturally: shell-quartet tiles are dealt round-robin to ranks
 inside the kernels (`fock_opts.rank/world`), every rank accumulates a partial result, and there is
 exactly one exchange step per SCF iteration -- an all-reduce of the N x N partial G.  In-core mode
-additionally reduce-scatters the packed supermatrix once after the build so that each rank streams
-only 1/world of it per iteration.
+replicates the one-off build and shards the per-iteration streaming of the packed supermatrix, so each
+rank reads only 1/world of it per iteration.
 """
 from __future__ import annotations
 
@@ -33,20 +33,13 @@ def device_view(ptr: int, n: int, device=None):
     return torch.as_tensor(_DevArray(ptr, n), device=device if device is not None else torch.device("cuda", torch.cuda.current_device()))
 
 
-def reduce_scatter_supermatrix(builder, rank: int, world: int):
-    """Sum the per-rank partial supermatrices; rank r keeps elements digest_ranges()[r]."""
-    import torch
-    import torch.distributed as dist
-
-    ptr, n_padded = builder.supermatrix_device()
+def shard_digestion(builder, rank: int, world: int):
+    """In-core mode: the (one-off, millisecond-scale) build is replicated on every rank and the
+    per-iteration streaming of the packed supermatrix is sharded -- rank r keeps digest_ranges()[r].
+    (Sharding the build instead would need a reduce-scatter of the whole packed tensor, 1.9 GB at
+    N=208, which costs more than the build.)  fock_eri_build already selects this range by default;
+    this helper exists for callers that want a different partition."""
     n = builder._L.fock_packed_len(builder.n)
-    chunk = (n + world - 1) // world
-    assert n_padded >= chunk * world, "supermatrix buffer is not padded for this world size"
-    full = device_view(ptr, chunk * world)
-    torch.cuda.synchronize()
-    out = full[rank * chunk : (rank + 1) * chunk]
-    dist.reduce_scatter_tensor(out, full, op=dist.ReduceOp.SUM)
-    torch.cuda.synchronize()
     begin, end = digest_ranges(n, world)[rank]
     builder.set_digest_range(begin, end)
 

@@ -131,9 +131,12 @@ int fock_one_electron(fock_ctx *ctx, int32_t n_nuclei, const double *nuclei_pos,
 /* Use a caller-provided cudaStream_t for all launches (NULL = the context's own stream). */
 int fock_set_stream(fock_ctx *ctx, void *cuda_stream);
 
-/* Multi-process in-core plumbing (one process per GPU): the supermatrix buffer, so the host
- * side can reduce-scatter it with its collective library, then the element range
- * [begin, end) of the packed supermatrix this rank streams in fock_build_g. */
+/* Multi-process plumbing (one process per GPU, `rank`/`world` in fock_opts).  Integral-direct
+ * mode shards the shell-quartet tiles over ranks.  In-core mode replicates the (one-off) build and
+ * shards the per-iteration streaming: after fock_eri_build rank r streams the r-th of `world`
+ * equal contiguous element ranges of the packed supermatrix; fock_set_digest_range overrides that
+ * range, fock_supermatrix_device exposes the buffer (fock_packed_len(N) doubles).  Either way
+ * fock_build_g returns a PARTIAL G that the caller sums with one all-reduce of N*N doubles. */
 int fock_supermatrix_device(fock_ctx *ctx, void **dev_ptr, size_t *n_elements);
 int fock_set_digest_range(fock_ctx *ctx, size_t begin, size_t end);
 

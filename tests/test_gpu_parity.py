@@ -236,3 +236,21 @@ def test_supermatrix_scatter_equals_gather_definition():
     with FockBuilder(fb, kernel=1) as b:
         g1 = b.eri_build().build_g(D)
     assert np.max(np.abs(g0 - g1)) <= 1e-12
+
+
+def test_two_rank_sharding_matches_oracle():
+    """World-size-2 run (one process per GPU, NCCL): tiles sharded, supermatrix reduce-scattered,
+    partial G all-reduced.  Needs two GPUs; the gloo test in test_host_cpu.py covers the host logic."""
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multi_gpu_check.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", script], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MULTI_GPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

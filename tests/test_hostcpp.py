@@ -1,0 +1,44 @@
+"""The header-only C++ mirror (fock_rs_b200/hostcpp/fock_b200.hpp) compiles against the C ABI and,
+on a GPU box, reproduces the oracle for H2/STO-3G (the molecule of the reference's test_integrals)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from fock_rs_b200 import _lib
+from fock_rs_b200.basis_set import BasisSet, flatten
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "build", "hostcpp_main")
+
+
+def _compile():
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "hostcpp_main.cpp"),
+                           "-o", EXE, "-L" + lib_dir, "-lfock_b200", "-Wl,-rpath," + lib_dir, "-Wl,-rpath,/usr/local/cuda/lib64"])
+
+
+def test_hostcpp_compiles_and_links():
+    _lib.load()
+    _compile()
+    assert os.path.exists(EXE)
+
+
+@pytest.mark.gpu
+def test_hostcpp_matches_oracle():
+    _compile()
+    out = subprocess.run([EXE], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().splitlines()
+    eris = [float(x) for x in lines[0].split()]
+    g = np.array([float(x) for x in lines[1].split()]).reshape(2, 2)
+    bs = BasisSet.named("STO-3G")
+    fb = flatten(bs.get((0.0, 0.0, 0.0), 1).basis + bs.get((0.0, 0.0, 1.2), 1).basis)
+    ob = oracle.OracleBasis.from_flat(fb)
+    want = [oracle.eri(ob, 0, 0, 0, 0), oracle.eri(ob, 1, 0, 1, 0), oracle.eri(ob, 1, 1, 0, 0)]
+    np.testing.assert_allclose(eris, want, rtol=0, atol=1e-12)
+    packed, _ = oracle.from_basis_packed(ob, oracle.FAITHFUL, fast=True)
+    np.testing.assert_allclose(g, oracle.build_g(packed, 2, np.eye(2)), rtol=0, atol=1e-12)
