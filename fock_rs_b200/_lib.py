@@ -24,7 +24,7 @@ EXPORTS = [
     "fock_default_opts", "fock_create", "fock_eri_build", "fock_eri_get", "fock_eri_export_packed", "fock_packed_len",
     "fock_eri_batch", "fock_build_g", "fock_build_g_device", "fock_one_electron", "fock_set_stream",
     "fock_supermatrix_device", "fock_set_digest_range", "fock_timings", "fock_stats", "fock_last_error", "fock_destroy",
-    "fock_abi_version", "fock_measure_fp64_peak",
+    "fock_abi_version", "fock_measure_fp64_peak", "fock_boys_batch",
 ]
 
 
@@ -97,5 +97,6 @@ def load():
     L.fock_destroy.restype = None
     L.fock_abi_version.restype = C.c_int
     L.fock_measure_fp64_peak.argtypes = [vp, dp]
+    L.fock_boys_batch.argtypes = [vp, dp, C.c_size_t, C.c_int32, dp]
     _lib = L
     return L

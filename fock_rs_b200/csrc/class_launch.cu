@@ -15,31 +15,26 @@ namespace {
 const int kClsLA[3] = {0, 1, 1}, kClsLB[3] = {0, 0, 1};
 
 template <int LA, int LB, int LC, int LD, int KC0, int KCN, class Sink>
-void launch_mode(const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, size_t smem, cudaStream_t st) {
-    const bool acc = mode & FOCK_MODE_BOYS_ACCURATE_BIT, fix = mode & FOCK_MODE_FIX_R_BIT;
-    if (!acc && !fix)
-        eri_class_kernel<LA, LB, LC, LD, false, false, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
-    else if (!acc && fix)
-        eri_class_kernel<LA, LB, LC, LD, false, true, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
-    else if (acc && !fix)
-        eri_class_kernel<LA, LB, LC, LD, true, false, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
+void launch_mode(const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, cudaStream_t st) {
+    const size_t smem = boys_smem_doubles(LA + LB + LC + LD, cl.boys_ni) * sizeof(double);
+    if (mode & FOCK_MODE_FIX_R_BIT)
+        eri_class_kernel<LA, LB, LC, LD, true, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
     else
-        eri_class_kernel<LA, LB, LC, LD, true, true, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
+        eri_class_kernel<LA, LB, LC, LD, false, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
 }
 
 template <class Sink>
 int launch_class(int cb, int ck, const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, cudaStream_t st) {
-    const size_t smem = 0;
     switch (cb * 3 + ck) {
-        case 0: launch_mode<0, 0, 0, 0, 0, 1>(cl, sink, mode, grid, smem, st); return 1;
-        case 3: launch_mode<1, 0, 0, 0, 0, 1>(cl, sink, mode, grid, smem, st); return 1;
-        case 4: launch_mode<1, 0, 1, 0, 0, 3>(cl, sink, mode, grid, smem, st); return 1;
-        case 6: launch_mode<1, 1, 0, 0, 0, 1>(cl, sink, mode, grid, smem, st); return 1;
-        case 7: launch_mode<1, 1, 1, 0, 0, 3>(cl, sink, mode, grid, smem, st); return 1;
+        case 0: launch_mode<0, 0, 0, 0, 0, 1>(cl, sink, mode, grid, st); return 1;
+        case 3: launch_mode<1, 0, 0, 0, 0, 1>(cl, sink, mode, grid, st); return 1;
+        case 4: launch_mode<1, 0, 1, 0, 0, 3>(cl, sink, mode, grid, st); return 1;
+        case 6: launch_mode<1, 1, 0, 0, 0, 1>(cl, sink, mode, grid, st); return 1;
+        case 7: launch_mode<1, 1, 1, 0, 0, 3>(cl, sink, mode, grid, st); return 1;
         case 8:  // (pp|pp): 81 accumulators do not fit one thread's registers -> three ket-component slices
-            launch_mode<1, 1, 1, 1, 0, 3>(cl, sink, mode, grid, smem, st);
-            launch_mode<1, 1, 1, 1, 3, 3>(cl, sink, mode, grid, smem, st);
-            launch_mode<1, 1, 1, 1, 6, 3>(cl, sink, mode, grid, smem, st);
+            launch_mode<1, 1, 1, 1, 0, 3>(cl, sink, mode, grid, st);
+            launch_mode<1, 1, 1, 1, 3, 3>(cl, sink, mode, grid, st);
+            launch_mode<1, 1, 1, 1, 6, 3>(cl, sink, mode, grid, st);
             return 3;
         default: return 0;
     }
@@ -47,15 +42,11 @@ int launch_class(int cb, int ck, const ClassLaunch &cl, const Sink &sink, int mo
 
 template <int LA, int LB, int KC0, int KCN>
 void launch_diag_mode(const DiagLaunch &dl, const DiagSink &sink, int mode, dim3 grid, cudaStream_t st) {
-    const bool acc = mode & FOCK_MODE_BOYS_ACCURATE_BIT, fix = mode & FOCK_MODE_FIX_R_BIT;
-    if (!acc && !fix)
-        eri_diag_kernel<LA, LB, false, false, KC0, KCN><<<grid, kClassThreads, 0, st>>>(dl, sink);
-    else if (!acc && fix)
-        eri_diag_kernel<LA, LB, false, true, KC0, KCN><<<grid, kClassThreads, 0, st>>>(dl, sink);
-    else if (acc && !fix)
-        eri_diag_kernel<LA, LB, true, false, KC0, KCN><<<grid, kClassThreads, 0, st>>>(dl, sink);
+    const size_t smem = boys_smem_doubles(2 * (LA + LB), dl.boys_ni) * sizeof(double);
+    if (mode & FOCK_MODE_FIX_R_BIT)
+        eri_diag_kernel<LA, LB, true, KC0, KCN><<<grid, kClassThreads, smem, st>>>(dl, sink);
     else
-        eri_diag_kernel<LA, LB, true, true, KC0, KCN><<<grid, kClassThreads, 0, st>>>(dl, sink);
+        eri_diag_kernel<LA, LB, false, KC0, KCN><<<grid, kClassThreads, smem, st>>>(dl, sink);
 }
 
 // sorted tables from the natural-order master: position i of a sublist takes natural pair perm[i]
@@ -124,8 +115,8 @@ int ClassEngine::run_diagonal(double *d_diag, std::string &err) {
         const Sublist &s = sd->sublists[si];
         const int n = (int)s.pair_ids.size();
         if (!n) continue;
-        DiagLaunch dl{d_bra_nat + s.bra_off, d_meta_nat + s.meta_off, dev->d_shell_bf, boys.lut, boys.tab, s.K, n};
-        dim3 grid((unsigned)((n + kClassWarps - 1) / kClassWarps));
+        DiagLaunch dl{d_bra_nat + s.bra_off, d_meta_nat + s.meta_off, dev->d_shell_bf, boys_poly, boys_ni, s.K, n};
+        dim3 grid((unsigned)std::min((n + kClassWarps - 1) / kClassWarps, num_sms * 4));
         if (s.cls == 0) {
             launch_diag_mode<0, 0, 0, 1>(dl, sink, mode, grid, stream);
             launches += 1;
@@ -149,7 +140,7 @@ int ClassEngine::run_diagonal(double *d_diag, std::string &err) {
 
 // With the diagonal on the host: per-pair max |(xy|xy)|, sort each sublist (descending), permute the
 // device tables accordingly.
-int ClassEngine::sort_by_diagonal(const std::vector<double> &h_diag, std::string &err) {
+int ClassEngine::sort_by_diagonal(const double *h_diag, std::string &err) {
     for (ShellPair &p : sd->pairs) {
         const Shell &A = sd->shells[p.A], &B = sd->shells[p.B];
         double m = 0.0;
@@ -168,12 +159,12 @@ int ClassEngine::sort_by_diagonal(const std::vector<double> &h_diag, std::string
         Sublist &s = sd->sublists[si];
         const std::vector<int> &nat = nat_ids[si];
         const int n = (int)nat.size();
-        std::vector<int> order(n);
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return sd->pairs[nat[x]].maxdiag > sd->pairs[nat[y]].maxdiag; });
+        std::vector<std::pair<double, int>> keyed(n);  // contiguous keys: cache-friendly sort
+        for (int i = 0; i < n; ++i) keyed[i] = std::make_pair(-sd->pairs[nat[i]].maxdiag, i);
+        std::sort(keyed.begin(), keyed.end());  // descending maxdiag, ties by natural index (deterministic)
         for (int i = 0; i < n; ++i) {
-            s.pair_ids[i] = nat[order[i]];
-            perm[s.meta_off / 2 + i] = order[i];
+            s.pair_ids[i] = nat[keyed[i].second];
+            perm[s.meta_off / 2 + i] = keyed[i].second;
         }
     }
     cudaMemcpyAsync(d_perm, perm, (dev->meta_ints / 2) * sizeof(int), cudaMemcpyHostToDevice, stream);
@@ -227,6 +218,35 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
             pl.ck = ck;
             pl.job_begin = (int)jobs.size();
             long long tiles_launch = 0;
+            // K-split threshold: one thread's primitive loop (class cost x depth, in instructions) may not
+            // exceed a quarter of the average work per resident thread of this launch, nor ~6000
+            // instructions when the launch is small -- otherwise it becomes the launch's critical path.
+            static const int kCost[3][3] = {{80, 0, 0}, {110, 200, 0}, {220, 600, 1000}};
+            double launch_work = 0.0;
+            for (int b = 0; b < ns; ++b) {
+                const Sublist &sb = sd->sublists[b];
+                if (sb.cls != cb || sb.pair_ids.empty()) continue;
+                for (int k = 0; k <= b; ++k) {
+                    const Sublist &sk = sd->sublists[k];
+                    if (sk.cls != ck || sk.pair_ids.empty()) continue;
+                    const int nb = (int)sb.pair_ids.size(), nk = (int)sk.pair_ids.size();
+                    double q = 0.0;
+                    if (screen == FOCK_SCREEN_OFF) {
+                        q = (b == k) ? 0.5 * nb * (nb + 1.0) : (double)nb * nk;
+                    } else {  // cheap estimate: sample 64 rows
+                        const int step = std::max(1, nb / 64);
+                        int cnt = 0;
+                        for (int r = 0; r < nb; r += step, ++cnt) {
+                            int nc = surviving_prefix(md[b][r], md[k], screen, thr);
+                            if (b == k) nc = std::min(nc, r + 1);
+                            q += nc;
+                        }
+                        q *= (double)nb / std::max(cnt, 1);
+                    }
+                    launch_work += q * sb.K * sk.K * kCost[cb][ck];
+                }
+            }
+            const double loop_limit = std::max(6000.0, 0.25 * launch_work / ((double)num_sms * 8 * kClassThreads));
             for (int b = 0; b < ns; ++b) {
                 const Sublist &sb = sd->sublists[b];
                 if (sb.cls != cb || sb.pair_ids.empty()) continue;
@@ -247,7 +267,11 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
                         quartets += (b == k) ? std::min(nc, r + 1) : nc;
                     }
                     prefix[nb] = quartets;
-                    const long long tiles = (quartets + 31) / 32;
+                    // K-split: keep one thread's loop below ~6000 instructions (class cost x depth)
+                    int S = 1;
+                    while (S < 32 && 2 * S <= sk.K && (double)sb.K * sk.K * kCost[cb][ck] / S > loop_limit) S *= 2;
+                    const long long per_tile = 32 / S;
+                    const long long tiles = (quartets + per_tile - 1) / per_tile;
                     plan_stats.shell_quartets_total += (b == k) ? (long long)nb * (nb + 1) / 2 : (long long)nb * nk;
                     plan_stats.shell_quartets += quartets;
                     plan_stats.prim_quartets += quartets * (long long)sb.K * sk.K;
@@ -269,6 +293,7 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
                     j.nb = nb;
                     j.nk_pad = sk.npad;
                     j.same_sublist = (b == k) ? 1 : 0;
+                    j.ksplit = S;
                     jobs.push_back(j);
                     job_table_off.push_back(off);
                     tiles_launch += tiles;
@@ -331,20 +356,39 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
 template <class Sink>
 int ClassEngine::run_plan(const Sink &sink, std::string &err) {
     int launches = 0;
-    for (const ClassPlanLaunch &pl : plan) {
+    // The class launches are independent (their sinks commute), so they are forked onto auxiliary
+    // streams, heaviest class first, and joined back: the long tail of one overlaps the next.
+    if (!ev_fork) {
+        cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+        for (int i = 0; i < kAuxStreams; ++i) {
+            cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
+        }
+    }
+    cudaEventRecord(ev_fork, stream);
+    for (int i = 0; i < kAuxStreams; ++i) cudaStreamWaitEvent(aux[i], ev_fork, 0);
+    int slot = 0;
+    for (int pi = (int)plan.size() - 1; pi >= 0; --pi) {  // plan is ordered light -> heavy
+        const ClassPlanLaunch &pl = plan[pi];
         ClassLaunch cl{};
         cl.jobs = d_jobs + pl.job_begin;
         cl.njobs = pl.njobs;
         cl.total_tiles = pl.total_tiles;
         cl.shell_bf = dev->d_shell_bf;
-        cl.boys_lut = boys.lut;
-        cl.boys_tab = boys.tab;
+        cl.boys_poly = boys_poly;
+        cl.boys_ni = boys_ni;
         cl.rank = plan_rank;
         cl.world = plan_world;
         const long long mine = (pl.total_tiles - plan_rank + plan_world - 1) / plan_world;  // warp tiles of this rank
         if (mine <= 0) continue;
-        dim3 grid((unsigned)((mine + kClassWarps - 1) / kClassWarps));
-        launches += launch_class(pl.cb, pl.ck, cl, sink, mode, grid, stream);
+        // persistent blocks: enough to fill the machine, each strides over the warp tiles
+        dim3 grid((unsigned)std::min<long long>((mine + kClassWarps - 1) / kClassWarps, (long long)num_sms * 8));
+        launches += launch_class(pl.cb, pl.ck, cl, sink, mode, grid, aux[slot % kAuxStreams]);
+        ++slot;
+    }
+    for (int i = 0; i < kAuxStreams; ++i) {
+        cudaEventRecord(ev_join[i], aux[i]);
+        cudaStreamWaitEvent(stream, ev_join[i], 0);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -366,6 +410,13 @@ ClassEngine::~ClassEngine() {
     if (h_perm) cudaFreeHost(h_perm);
     if (h_table) cudaFreeHost(h_table);
     if (h_jobs) cudaFreeHost(h_jobs);
+    if (ev_fork) {
+        cudaEventDestroy(ev_fork);
+        for (int i = 0; i < kAuxStreams; ++i) {
+            cudaStreamDestroy(aux[i]);
+            cudaEventDestroy(ev_join[i]);
+        }
+    }
 }
 
 }  // namespace fock

@@ -32,7 +32,9 @@ struct ClassPlanLaunch {
 struct ClassEngine {
     ShellData *sd = nullptr;
     PairTablesDev *dev = nullptr;
-    BoysTables boys{};
+    const double *boys_poly = nullptr;  // device, per-interval polynomial table of the active mode
+    int boys_ni = 200;
+    int num_sms = 148;
     cudaStream_t stream = nullptr;
     int mode = 0;
 
@@ -58,9 +60,13 @@ struct ClassEngine {
     int plan_screen = -1, plan_rank = -1, plan_world = -1;
     double plan_thr = 0;
 
+    static constexpr int kAuxStreams = 4;
+    cudaStream_t aux[kAuxStreams] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kAuxStreams] = {};
+
     int upload_master(std::string &err);                 // once, after build_pairs
     int run_diagonal(double *d_diag, std::string &err);  // returns launches or -1
-    int sort_by_diagonal(const std::vector<double> &h_diag, std::string &err);  // returns launches or -1
+    int sort_by_diagonal(const double *h_diag, std::string &err);  // returns launches or -1
     int make_plan(int screen, double thr, int rank, int world, std::string &err);
     template <class Sink>
     int run_plan(const Sink &sink, std::string &err);  // returns launches or -1

@@ -6,6 +6,7 @@
 #include <memory>
 #include <new>
 
+#include "boys_tables.h"
 #include "class_launch.h"
 #include "context.h"
 #include "eri_class.cuh"
@@ -43,8 +44,10 @@ struct ClassState {
     ClassStats stats;
     unsigned char *d_bf_class_ok = nullptr;
     unsigned long long *d_counter = nullptr;
+    double *d_boys_poly = nullptr;
     double *h_diag = nullptr;  // pinned image of d_diag
     cudaEvent_t ev_diag = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // bracket the class-kernel launches
 };
 
 ClassState *cls(fock_ctx *ctx);
@@ -198,7 +201,18 @@ int fock_create(const fock_basis *b, const fock_opts *opts_in, fock_ctx **out) {
         ClassState *cs = &ctx->cs;
         cs->engine.sd = &ctx->shells;
         cs->engine.dev = &ctx->pairs;
-        cs->engine.boys = ctx->boys();
+        {
+            std::vector<double> poly;
+            const bool accurate = (o.mode & FOCK_MODE_BOYS_ACCURATE) != 0;
+            if (accurate) make_boys_poly_accurate(poly); else make_boys_poly_faithful(kBoysLut, poly);
+            FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&cs->d_boys_poly, poly.size() * sizeof(double)));
+            FOCK_CUDA_TRY(ctx, cudaMemcpy(cs->d_boys_poly, poly.data(), poly.size() * sizeof(double), cudaMemcpyHostToDevice));
+            cs->engine.boys_poly = cs->d_boys_poly;
+            cs->engine.boys_ni = accurate ? kBoysAccIntervals : kBoysPolyIntervals;
+            cudaDeviceProp prop;
+            FOCK_CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+            cs->engine.num_sms = prop.multiProcessorCount;
+        }
         cs->engine.stream = ctx->stream;
         cs->engine.mode = o.mode;
         if (!ctx->shells.pairs.empty() && cs->engine.upload_master(err)) {
@@ -235,12 +249,14 @@ void fock_destroy(fock_ctx *c) {
     void *ptrs[] = {ctx->d_center, ctx->d_angular, ctx->d_primoff, ctx->d_exp,  ctx->d_coef, ctx->d_boys_lut,
                     ctx->d_boys_tab, ctx->d_diag,   ctx->d_V,       ctx->d_P,    ctx->d_dvec, ctx->d_yvec,
                     ctx->d_D,      ctx->d_G,       ctx->pairs.d_bra, ctx->pairs.d_ket, ctx->pairs.d_meta,
-                    ctx->pairs.d_shell_bf, ctx->pairs.d_maxdiag, ctx->cs.d_bf_class_ok, ctx->cs.d_counter};
+                    ctx->pairs.d_shell_bf, ctx->pairs.d_maxdiag, ctx->cs.d_bf_class_ok, ctx->cs.d_counter, ctx->cs.d_boys_poly};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->cs.h_diag) cudaFreeHost(ctx->cs.h_diag);
     if (ctx->cs.ev_diag) cudaEventDestroy(ctx->cs.ev_diag);
+    if (ctx->cs.ev_k0) cudaEventDestroy(ctx->cs.ev_k0);
+    if (ctx->cs.ev_k1) cudaEventDestroy(ctx->cs.ev_k1);
     for (int i = 0; i < EV_COUNT; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -265,6 +281,8 @@ static int diagonal_launch(fock_ctx *ctx, int *launches) {
     std::string err;
     if (!cs->h_diag) FOCK_CUDA_TRY(ctx, cudaMallocHost((void **)&cs->h_diag, ctx->npair * sizeof(double)));
     if (!cs->ev_diag) FOCK_CUDA_TRY(ctx, cudaEventCreateWithFlags(&cs->ev_diag, cudaEventDisableTiming));
+    if (!cs->ev_k0) FOCK_CUDA_TRY(ctx, cudaEventCreate(&cs->ev_k0));
+    if (!cs->ev_k1) FOCK_CUDA_TRY(ctx, cudaEventCreate(&cs->ev_k1));
     FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_diag, 0, ctx->npair * sizeof(double), st));
     if (!ctx->shells.pairs.empty()) {
         const int l = cs->engine.run_diagonal(ctx->d_diag, err);
@@ -291,8 +309,7 @@ static int diagonal_finish(fock_ctx *ctx, int *launches) {
     if (!ctx->shells.pairs.empty()) {
         const auto t0 = std::chrono::steady_clock::now();
         std::string err;
-        std::vector<double> h(cs->h_diag, cs->h_diag + ctx->npair);
-        const int l = cs->engine.sort_by_diagonal(h, err);
+        const int l = cs->engine.sort_by_diagonal(cs->h_diag, err);
         if (l < 0) {
             ctx->err = err;
             return FOCK_ERR_CUDA;
@@ -362,7 +379,9 @@ int fock_eri_build(fock_ctx *ctx) {
             std::string err;
             FOCK_TRY(make_plan_timed(ctx, thr, b_rank, b_world));
             TensorSink sink{Vp, Pp, ctx->d_diag, thr, ctx->opts.screen};
+            FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_k0, st));
             const int l = cs->engine.run_plan(sink, err);
+            FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_k1, st));
             if (l < 0) {
                 ctx->err = err;
                 return FOCK_ERR_CUDA;
@@ -549,7 +568,9 @@ int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev) {
             std::string err;
             FOCK_TRY(make_plan_timed(ctx, thr, ctx->opts.rank, ctx->opts.world));
             DirectSink sink{ctx->d_yvec, ctx->d_dvec, ctx->d_diag, thr, ctx->opts.screen};
+            FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_k0, st));
             const int l = cs->engine.run_plan(sink, err);
+            FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_k1, st));
             if (l < 0) {
                 ctx->err = err;
                 return FOCK_ERR_CUDA;
@@ -656,6 +677,33 @@ int fock_set_digest_range(fock_ctx *ctx, size_t begin, size_t end) {
     return FOCK_OK;
 }
 
+int fock_boys_batch(fock_ctx *ctx, const double *t, size_t n, int32_t order, double *values) {
+    if (!ctx || (!t && n) || (!values && n)) return FOCK_ERR_BAD_ARG;
+    if (order < 0 || order > 10) {
+        ctx->err = "Boys-Function order is higher than max tabulated order 10";
+        return FOCK_ERR_BOYS_ORDER;
+    }
+    if (n == 0) return FOCK_OK;
+    FOCK_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    double *d = nullptr;
+    FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&d, 2 * n * sizeof(double)));
+    cudaStream_t st = ctx->stream;
+    cudaMemcpyAsync(d, t, n * sizeof(double), cudaMemcpyHostToDevice, st);
+    ClassState *cs = cls(ctx);
+    if (order < kBoysPolyOrders)
+        boys_poly_batch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(cs->d_boys_poly, cs->engine.boys_ni, d, n, order, d + n);
+    else
+        boys_generic_batch_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ctx->boys(), ctx->opts.mode, d, n, order, d + n);
+    cudaMemcpyAsync(values, d + n, n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("fock_boys_batch: ") + cudaGetErrorString(e);
+        return FOCK_ERR_CUDA;
+    }
+    return FOCK_OK;
+}
+
 int fock_measure_fp64_peak(fock_ctx *ctx, double *tflops) {
     if (!ctx || !tflops) return FOCK_ERR_BAD_ARG;
     FOCK_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -684,6 +732,12 @@ int fock_timings(fock_ctx *ctx, double *ms, int32_t n) {
     if (ctx->built && ctx->ev[EV_F] && cudaEventQuery(ctx->ev[EV_F]) == cudaSuccess) {
         float t = 0;
         if (cudaEventElapsedTime(&t, ctx->ev[EV_E], ctx->ev[EV_F]) == cudaSuccess) ctx->timings[3] = t;
+    }
+    {
+        ClassState *cs = cls(ctx);
+        float t = 0;
+        if (cs->ev_k1 && cudaEventQuery(cs->ev_k1) == cudaSuccess && cudaEventElapsedTime(&t, cs->ev_k0, cs->ev_k1) == cudaSuccess)
+            ctx->timings[7] = t;
     }
     cudaGetLastError();
     for (int i = 0; i < n && i < 8; ++i) ms[i] = ctx->timings[i];

@@ -3,6 +3,7 @@
 // matrix-vector product) that replaces the reference's per-iteration G loop.
 #pragma once
 #include "device_math.cuh"
+#include "eri_class.cuh"
 #include "eri_generic.cuh"
 #include "super_scatter.cuh"
 
@@ -209,6 +210,47 @@ __global__ void __launch_bounds__(kSymvThreads) symv_packed_kernel(const double 
         for (int w = 0; w < kSymvThreads / 32; ++w) v += s_red[w][tid];
         if (v != 0.0) atomicAdd(y + r0 + tid, v);
     }
+}
+
+// Boys function for a batch of arguments through the same tables the class kernels use (tests).
+__global__ void boys_poly_batch_kernel(const double *__restrict__ poly, int ni, const double *__restrict__ T, size_t n,
+                                       int order, double *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double F0[1], F1[2], F2[3], F3[4], F4[5];
+    // global-memory table with the shared-memory layout of the order requested
+    switch (order) {
+        case 0: boys_poly_eval<0>(T[i], F0, poly, ni); out[i] = F0[0]; break;
+        case 1: boys_poly_eval<1>(T[i], F1, poly, ni); out[i] = F1[1]; break;
+        default: {
+            // L >= 2 reads one table + the exp(-mid) vector laid out behind it: assemble on the fly
+            const int L = order;
+            const double tmax = (double)ni * 0.15;
+            const double t = T[i];
+            if (t < tmax) {
+                const int k = (int)(t * (200.0 / 30.0));
+                const double x = t - ((double)k + 0.5) * 0.15;
+                const double *c = poly + (size_t)L * 8 * ni + k;
+                double r = c[7 * ni];
+                for (int j = 6; j >= 0; --j) r = fma(r, x, c[j * ni]);
+                out[i] = r;
+            } else {
+                if (L == 2) { boys_poly_eval<2>(t, F2, poly, ni); out[i] = F2[2]; }
+                else if (L == 3) { boys_poly_eval<3>(t, F3, poly, ni); out[i] = F3[3]; }
+                else { boys_poly_eval<4>(t, F4, poly, ni); out[i] = F4[4]; }
+            }
+        }
+    }
+}
+
+// ---- Boys function through the generic evaluators (orders the class tables do not carry)
+__global__ void boys_generic_batch_kernel(BoysTables bt, int mode, const double *__restrict__ T, size_t n, int order,
+                                          double *__restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double F[11];
+    if (mode & FOCK_MODE_BOYS_ACCURATE_BIT) boys_accurate(T[i], order, F, bt.tab); else boys_faithful(T[i], order, F, bt.lut);
+    out[i] = F[order];
 }
 
 // ---- FP64 FMA peak probe: 8 independent register chains per thread.

@@ -105,6 +105,13 @@ class FockBuilder:
         self._check(self._L.fock_eri_batch(self._ctx, q.ctypes.data_as(C.POINTER(C.c_int32)), q.shape[0], _dp(out)))
         return out
 
+    def boys(self, t, order: int) -> np.ndarray:
+        """`boys::boys(t, n)` (boys/src/lib.rs:58) for an array of arguments, evaluated on the device."""
+        tt = np.ascontiguousarray(t, dtype=np.float64).ravel()
+        out = np.empty_like(tt)
+        self._check(self._L.fock_boys_batch(self._ctx, _dp(tt), tt.size, int(order), _dp(out)))
+        return out
+
     def build_g(self, D) -> np.ndarray:
         """G = J - K/2 for a symmetric density (host buffers, column-major like DMatrix)."""
         Dc = np.asfortranarray(D, dtype=np.float64)
@@ -147,7 +154,7 @@ class FockBuilder:
         ms = (C.c_double * 8)()
         self._check(self._L.fock_timings(self._ctx, ms, 8))
         return {"diag_ms": ms[0], "eri_ms": ms[1], "supermatrix_ms": ms[2], "g_device_ms": ms[3], "g_e2e_ms": ms[4],
-                "host_sort_ms": ms[5], "host_plan_ms": ms[6]}
+                "host_sort_ms": ms[5], "host_plan_ms": ms[6], "class_kernels_ms": ms[7]}
 
     def stats(self) -> dict:
         s = (C.c_int64 * 16)()

@@ -113,6 +113,11 @@ size_t fock_packed_len(int32_t n_basis);
  * `quartets[n][4]`; no screening.  Evaluated on the GPU by the generic per-function kernel. */
 int fock_eri_batch(fock_ctx *ctx, const int32_t *quartets, size_t n, double *values);
 
+/* boys::boys(t, n) (boys/src/lib.rs:58-81) for a batch of arguments, on the device, in the context's
+ * Boys mode.  Orders 0..4 go through the per-interval tables the class kernels use, higher orders
+ * through the generic evaluator.  order > 10 -> FOCK_ERR_BOYS_ORDER (the reference asserts). */
+int fock_boys_batch(fock_ctx *ctx, const double *t, size_t n, int32_t order, double *values);
+
 /* The per-iteration G build, scf/src/lib.rs:177-185 (inside utils::hermitian, scf/src/utils.rs:25-28):
  *   G_ij = sum_xy D[(x,y)] * ((ij|xy) - 1/2 (ix|jy)),   G symmetric.
  * D must be symmetric (the reference's density is, by construction).  With world > 1 the
@@ -141,8 +146,10 @@ int fock_supermatrix_device(fock_ctx *ctx, void **dev_ptr, size_t *n_elements);
 int fock_set_digest_range(fock_ctx *ctx, size_t begin, size_t end);
 
 /* Timings of the last fock_eri_build / fock_build_g in milliseconds (CUDA events):
- *   [0] pair/diagonal pass  [1] ERI class kernels  [2] supermatrix formation
- *   [3] last G build (device part)  [4] last G build incl. host<->device copies */
+ *   [0] pair/diagonal pass  [1] tensor build after the diagonal launch (memsets, host sort/plan, class kernels)  [2] supermatrix gather (kernel=1 only)
+ *   [3] last G build (device part)  [4] last G build incl. host<->device copies
+ *   [5] host: sublist sorting  [6] host: job/tile plan  [7] class ERI kernels only (events around
+ *   the class launches of the last build or direct G build) */
 int fock_timings(fock_ctx *ctx, double *ms, int32_t n);
 
 /* Counters: [0] N  [1] shells  [2] shell pairs  [3] unique shell quartets (unscreened)

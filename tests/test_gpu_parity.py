@@ -254,3 +254,26 @@ def test_two_rank_sharding_matches_oracle():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                           "--master-port", "29533", script], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "MULTI_GPU_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("mode,exact", [(_lib.MODE_FAITHFUL, False), (_lib.MODE_ACCURATE, True)])
+def test_device_boys_function_matches_reference(mode, exact):
+    """boys::boys(t, n) on the device (the per-interval tables of the class kernels for n <= 4, the
+    generic evaluator above) against the oracle on a dense grid incl. the T = 30 switch-over."""
+    rng = np.random.default_rng(3)
+    t = np.concatenate([rng.uniform(0.0, 36.0, 20000), np.arange(0, 200) * 0.15, np.arange(1, 200) * 0.15 * (1 - 1e-16),
+                        [0.0, 1e-17, 1e-9, 29.99, 29.999999, 30.0, 30.0000001, 45.0, 100.0, 250.0]])
+    with FockBuilder(flat_for("water", "STO-3G"), mode=mode) as b:
+        for n in range(0, 11):
+            got = b.boys(t, n)
+            want = np.array([(oracle.boys_exact if exact else oracle.boys)(float(x), n) for x in t])
+            assert np.max(np.abs(got - want)) <= 2e-15, n
+            # relative check where the value is not negligible; 1e-9 because the accurate mode switches to the
+            # asymptotic form at T = 40, dropping terms of order exp(-40) (absolute 1e-19)
+            big = np.abs(want) > 1e-12
+            assert np.max(np.abs(got - want)[big] / np.abs(want)[big]) <= 1e-9, n
+            small_t = big & (t < 29.0)
+            assert np.max(np.abs(got - want)[small_t] / np.abs(want)[small_t]) <= 1e-13, n
+        with pytest.raises(_lib.FockError) as ei:
+            b.boys(t[:4], 11)
+        assert ei.value.code == _lib.ERR_BOYS_ORDER
