@@ -170,6 +170,15 @@ __host__ __device__ __forceinline__ size_t packed_index(size_t x, size_t y, size
     return xy >= zw ? tri(xy, zw) : tri(zw, xy);
 }
 
+// Supermatrix storage: packed lower triangle whose ROWS are padded to a multiple of 4 doubles, so that
+// every row starts on a 32-byte sector boundary and can be streamed with aligned 128-bit loads.
+// Row r = 4a + b starts at 4(a+1)(2a+b); element (r, c), c <= r, sits at prow(r) + c.
+__host__ __device__ __forceinline__ size_t prow(size_t r) {
+    const size_t a = r >> 2, b = r & 3;
+    return 4 * (a + 1) * (2 * a + b);
+}
+__host__ __device__ __forceinline__ size_t ptri(size_t r, size_t c) { return prow(r) + c; }
+
 // Inverse of tri(): row r with tri(r,0) <= k < tri(r+1,0), and the column.
 __host__ __device__ __forceinline__ void untri(size_t k, size_t &r, size_t &c) {
     size_t g = (size_t)((sqrt(8.0 * (double)k + 1.0) - 1.0) * 0.5);

@@ -225,7 +225,7 @@ int fock_create(const fock_basis *b, const fock_opts *opts_in, fock_ctx **out) {
         FOCK_CUDA_TRY(ctx, cudaMemcpy(cs->d_bf_class_ok, ok.data(), n, cudaMemcpyHostToDevice));
         FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&cs->d_counter, sizeof(unsigned long long)));
         ctx->digest_begin = 0;
-        ctx->digest_end = ctx->nelem;
+        ctx->digest_end = prow(ctx->npair);
         ctx->stats[0] = n;
         ctx->stats[1] = (int64_t)ctx->shells.shells.size();
         ctx->stats[2] = (int64_t)(ctx->shells.shells.size() * (ctx->shells.shells.size() + 1) / 2);
@@ -359,7 +359,7 @@ int fock_eri_build(fock_ctx *ctx) {
         // default path scatters every integral into P as it is produced (V only if keep_eri).
         const bool gather = ctx->opts.kernel == 1;
         const bool want_v = ctx->opts.keep_eri || gather;
-        const size_t padded = ctx->nelem;
+        const size_t padded = prow(ctx->npair) + 8;  // row-padded supermatrix (ptri layout) + slack
         if (want_v && !ctx->d_V) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_V, ctx->nelem * sizeof(double)));
         if (!ctx->d_P) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_P, padded * sizeof(double)));
         if (want_v) FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_V, 0, ctx->nelem * sizeof(double), st));
@@ -428,9 +428,10 @@ int fock_eri_build(fock_ctx *ctx) {
     }
     if (ctx->opts.storage == FOCK_STORAGE_INCORE && ctx->opts.world > 1) {
         // default sharding of the digestion: equal contiguous element ranges of the packed supermatrix
-        const size_t chunk = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
-        ctx->digest_begin = std::min(ctx->nelem, chunk * (size_t)ctx->opts.rank);
-        ctx->digest_end = std::min(ctx->nelem, chunk * ((size_t)ctx->opts.rank + 1));
+        const size_t total = prow(ctx->npair);
+        const size_t chunk = ((total + ctx->opts.world - 1) / ctx->opts.world + 3) / 4 * 4;  // whole 32-byte sectors
+        ctx->digest_begin = std::min(total, chunk * (size_t)ctx->opts.rank);
+        ctx->digest_end = std::min(total, chunk * ((size_t)ctx->opts.rank + 1));
     }
     ctx->stats[6] = launches;
     ctx->built = true;
@@ -531,10 +532,19 @@ int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev) {
         }
         pack_density_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(D_dev, ctx->N, ctx->d_dvec, ctx->d_yvec, ctx->npair);
         // rows that intersect [digest_begin, digest_end)
-        size_t r_first = 0, r_last = ctx->npair - 1, c;
+        size_t r_first = 0, r_last = ctx->npair - 1;
         if (ctx->digest_end > ctx->digest_begin) {
-            untri(ctx->digest_begin, r_first, c);
-            untri(ctx->digest_end - 1, r_last, c);
+            // rows that intersect the padded element range: largest r with prow(r) <= e
+            auto row_of = [&](size_t e) {
+                size_t lo = 0, hi = ctx->npair - 1;
+                while (lo < hi) {
+                    const size_t mid = (lo + hi + 1) / 2;
+                    if (prow(mid) <= e) lo = mid; else hi = mid - 1;
+                }
+                return lo;
+            };
+            r_first = row_of(ctx->digest_begin);
+            r_last = row_of(ctx->digest_end - 1);
             r_first = r_first / kSymvRB * kSymvRB;
             const size_t nstrips = (r_last - r_first) / kSymvRB + 1;
             const size_t nchunks = r_last / kSymvCB + 1;
@@ -666,12 +676,12 @@ int fock_supermatrix_device(fock_ctx *ctx, void **dev_ptr, size_t *n_elements) {
         return FOCK_ERR_STATE;
     }
     *dev_ptr = ctx->d_P;
-    *n_elements = ctx->nelem;
+    *n_elements = prow(ctx->npair);  // row-padded layout, see device_math.cuh: prow()
     return FOCK_OK;
 }
 
 int fock_set_digest_range(fock_ctx *ctx, size_t begin, size_t end) {
-    if (!ctx || begin > end || end > ctx->nelem) return FOCK_ERR_BAD_ARG;
+    if (!ctx || begin > end || end > prow(ctx->npair)) return FOCK_ERR_BAD_ARG;
     ctx->digest_begin = begin;
     ctx->digest_end = end;
     return FOCK_OK;

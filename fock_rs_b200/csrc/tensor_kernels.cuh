@@ -103,7 +103,7 @@ __global__ void supermatrix_kernel(const double *__restrict__ V, double *__restr
     untri(e, ij, kl);
     untri(ij, i, j);
     untri(kl, k, l);
-    P[e] = V[e] - 0.25 * V[packed_index(i, k, j, l)] - 0.25 * V[packed_index(i, l, j, k)];
+    P[ptri(ij, kl)] = V[e] - 0.25 * V[packed_index(i, k, j, l)] - 0.25 * V[packed_index(i, l, j, k)];
 }
 
 // ---- density packing: d[tri(k,l)] = D_kl + D_lk (k != l), D_kk (k == l); D column-major N x N.
@@ -124,15 +124,16 @@ __global__ void unpack_result_kernel(const double *__restrict__ y, int n, double
     G[idx] = y[i >= j ? tri(i, j) : tri(j, i)];
 }
 
-// ---- digestion: y += P_sym * d over the packed lower triangle, elements [e_begin, e_end).
-// A block takes a strip of RB rows and a chunk of THREADS*M columns; lane-consecutive threads read
-// consecutive columns of one row (coalesced), keep RB row partials and M column partials in
-// registers, and flush with one atomic per column per strip and one per row per block.
+// ---- digestion: y += P_sym * d over the row-padded packed lower triangle (ptri layout), padded
+// elements [e_begin, e_end).  A block takes a strip of RB rows and a chunk of THREADS*2*M columns;
+// consecutive threads read consecutive 16-byte column pairs of one row (aligned, coalesced 128-bit
+// streaming loads), keep RB row partials and 2*M column partials in registers, and flush with one
+// atomic per column per strip and one per row per block.
 // Algorithmic traffic: 8 bytes per stored element, read exactly once.
 constexpr int kSymvRB = 16;
-constexpr int kSymvM = 4;
+constexpr int kSymvM = 2;  // 128-bit loads per thread per row
 constexpr int kSymvThreads = 256;
-constexpr int kSymvCB = kSymvThreads * kSymvM;
+constexpr int kSymvCB = kSymvThreads * kSymvM * 2;
 
 __global__ void __launch_bounds__(kSymvThreads) symv_packed_kernel(const double *__restrict__ P, const double *__restrict__ d,
                                                                   double *__restrict__ y, size_t np, size_t e_begin,
@@ -143,33 +144,36 @@ __global__ void __launch_bounds__(kSymvThreads) symv_packed_kernel(const double 
     const size_t rlast = (r0 + kSymvRB <= np ? r0 + kSymvRB : np) - 1;
     if (c0 > rlast) return;
     // skip blocks entirely outside [e_begin, e_end)
-    if (tri(rlast, rlast) < e_begin || tri(r0, 0) >= e_end) return;
+    if (ptri(rlast, rlast) < e_begin || prow(r0) >= e_end) return;
     const int tid = threadIdx.x;
     __shared__ double s_drow[kSymvRB];
     __shared__ double s_red[kSymvThreads / 32][kSymvRB];
     if (tid < kSymvRB) s_drow[tid] = (r0 + tid < np) ? d[r0 + tid] : 0.0;
-    double dcol[kSymvM], colsum[kSymvM], rowsum[kSymvRB];
+    double dcol[kSymvM][2], colsum[kSymvM][2], rowsum[kSymvRB];
     size_t col[kSymvM];
 #pragma unroll
     for (int m = 0; m < kSymvM; ++m) {
-        col[m] = c0 + (size_t)m * kSymvThreads + tid;
-        dcol[m] = col[m] < np ? d[col[m]] : 0.0;
-        colsum[m] = 0.0;
+        col[m] = c0 + ((size_t)m * kSymvThreads + tid) * 2;
+        dcol[m][0] = col[m] < np ? d[col[m]] : 0.0;
+        dcol[m][1] = col[m] + 1 < np ? d[col[m] + 1] : 0.0;
+        colsum[m][0] = colsum[m][1] = 0.0;
     }
 #pragma unroll
     for (int r = 0; r < kSymvRB; ++r) rowsum[r] = 0.0;
     __syncthreads();
-    const bool interior = (c0 + kSymvCB <= r0) && tri(r0, 0) >= e_begin && tri(rlast, rlast) < e_end && (r0 + kSymvRB <= np);
+    const bool interior = (c0 + kSymvCB <= r0) && prow(r0) >= e_begin && ptri(rlast, rlast) < e_end && (r0 + kSymvRB <= np);
     if (interior) {
 #pragma unroll
         for (int r = 0; r < kSymvRB; ++r) {
-            const double *rowp = P + tri(r0 + r, 0);
+            const double *rowp = P + prow(r0 + r);
             const double dr = s_drow[r];
 #pragma unroll
             for (int m = 0; m < kSymvM; ++m) {
-                const double v = __ldcs(rowp + col[m]);
-                rowsum[r] = fma(v, dcol[m], rowsum[r]);
-                colsum[m] = fma(v, dr, colsum[m]);
+                const double2 v = __ldcs(reinterpret_cast<const double2 *>(rowp + col[m]));
+                rowsum[r] = fma(v.x, dcol[m][0], rowsum[r]);
+                rowsum[r] = fma(v.y, dcol[m][1], rowsum[r]);
+                colsum[m][0] = fma(v.x, dr, colsum[m][0]);
+                colsum[m][1] = fma(v.y, dr, colsum[m][1]);
             }
         }
     } else {
@@ -177,24 +181,35 @@ __global__ void __launch_bounds__(kSymvThreads) symv_packed_kernel(const double 
         for (int r = 0; r < kSymvRB; ++r) {
             const size_t row = r0 + r;
             if (row < np) {
-                const size_t off = tri(row, 0);
+                const size_t off = prow(row);
                 const double dr = s_drow[r];
 #pragma unroll
                 for (int m = 0; m < kSymvM; ++m) {
                     const size_t c = col[m];
-                    const size_t e = off + c;
-                    if (c <= row && e >= e_begin && e < e_end) {
-                        const double v = __ldcs(P + e);
-                        rowsum[r] = fma(v, dcol[m], rowsum[r]);
-                        if (c != row) colsum[m] = fma(v, dr, colsum[m]);
+                    // rows are padded to 4 doubles, so the 16-byte pair starting at an even c <= row lies inside it
+                    const size_t e0 = off + c;
+                    if (c <= row && e0 + 1 >= e_begin && e0 < e_end) {
+                        const double2 v = __ldcs(reinterpret_cast<const double2 *>(P + e0));
+                        const bool in0 = e0 >= e_begin;
+                        const bool in1 = c + 1 <= row && e0 + 1 < e_end;
+                        if (in0) {
+                            rowsum[r] = fma(v.x, dcol[m][0], rowsum[r]);
+                            if (c != row) colsum[m][0] = fma(v.x, dr, colsum[m][0]);
+                        }
+                        if (in1) {
+                            rowsum[r] = fma(v.y, dcol[m][1], rowsum[r]);
+                            if (c + 1 != row) colsum[m][1] = fma(v.y, dr, colsum[m][1]);
+                        }
                     }
                 }
             }
         }
     }
 #pragma unroll
-    for (int m = 0; m < kSymvM; ++m)
-        if (col[m] < np && colsum[m] != 0.0) atomicAdd(y + col[m], colsum[m]);
+    for (int m = 0; m < kSymvM; ++m) {
+        if (col[m] < np && colsum[m][0] != 0.0) atomicAdd(y + col[m], colsum[m][0]);
+        if (col[m] + 1 < np && colsum[m][1] != 0.0) atomicAdd(y + col[m] + 1, colsum[m][1]);
+    }
     const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
     for (int r = 0; r < kSymvRB; ++r) {

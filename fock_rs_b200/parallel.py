@@ -39,7 +39,7 @@ def shard_digestion(builder, rank: int, world: int):
     (Sharding the build instead would need a reduce-scatter of the whole packed tensor, 1.9 GB at
     N=208, which costs more than the build.)  fock_eri_build already selects this range by default;
     this helper exists for callers that want a different partition."""
-    n = builder._L.fock_packed_len(builder.n)
+    _, n = builder.supermatrix_device()  # row-padded length
     begin, end = digest_ranges(n, world)[rank]
     builder.set_digest_range(begin, end)
 

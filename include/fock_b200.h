@@ -140,7 +140,7 @@ int fock_set_stream(fock_ctx *ctx, void *cuda_stream);
  * mode shards the shell-quartet tiles over ranks.  In-core mode replicates the (one-off) build and
  * shards the per-iteration streaming: after fock_eri_build rank r streams the r-th of `world`
  * equal contiguous element ranges of the packed supermatrix; fock_set_digest_range overrides that
- * range, fock_supermatrix_device exposes the buffer (fock_packed_len(N) doubles).  Either way
+ * range, fock_supermatrix_device exposes the buffer and its length (rows padded to 4 doubles).  Either way
  * fock_build_g returns a PARTIAL G that the caller sums with one all-reduce of N*N doubles. */
 int fock_supermatrix_device(fock_ctx *ctx, void **dev_ptr, size_t *n_elements);
 int fock_set_digest_range(fock_ctx *ctx, size_t begin, size_t end);
