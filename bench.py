@@ -323,6 +323,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     agree = float(np.max(np.abs(G.cpu().numpy().T - g_host)))
 
+    others = []
+    if not args.no_other_configs:
+        # all ranks take part (sharded runs); rank 0 reports
+        others.append(quick_config("benzene", "incore", "ref", rank, world, local))
+        others.append(quick_config("alkane40", "direct", "ref", rank, world, local))
     if rank == 0:
         eri_tf = st["model_flops"] / (tm["class_kernels_ms"] * 1e-3) * 1e-12 if tm["class_kernels_ms"] > 0 else 0.0
         g_gbs = 8.0 * nelem / world / max(tm["g_device_ms"], 1e-9) * 1e-6
@@ -349,6 +354,7 @@ def run_ours(args):
                       "prim_quartets_evaluated": st["prim_quartets_evaluated"], "model_flops": st["model_flops"], "warp_tiles": st["warp_tiles"], "device_vs_host_path_max_abs_diff": agree},
             "fp64_peak_tflops_measured": fp64_peak,
         }
+        line["other_configs"] = others
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.workload, args.screen == "ref", args.cpu_budget, nq).items() if k not in ("checksum",)}
         print(json.dumps(line))
@@ -356,6 +362,55 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def quick_config(workload, storage, screen, rank, world, local, steps=3):
+    """Secondary configs reported beside the headline workload (same step definition, device-resident D/G)."""
+    import torch
+
+    from fock_rs_b200 import _lib, parallel
+    from fock_rs_b200.fock import FockBuilder
+
+    flat = load_flat(workload)
+    n = flat.n_basis
+    nq, _ = unique_shell_quartets(flat)
+    st_mode = _lib.STORAGE_INCORE if storage == "incore" else _lib.STORAGE_DIRECT
+    b = FockBuilder(flat, screen=_lib.SCREEN_REFERENCE if screen == "ref" else _lib.SCREEN_OFF, storage=st_mode, device=local, rank=rank,
+                    world=world, keep_eri=False)
+    stream = torch.cuda.current_stream()
+    b.set_stream(stream.cuda_stream)
+    rng = np.random.default_rng(20261017)
+    Dh = rng.uniform(-1.0, 1.0, (n, n))
+    D = torch.from_numpy(0.5 * (Dh + Dh.T)).cuda()
+    G = torch.empty_like(D)
+
+    def step():
+        b.eri_build()
+        b.build_g_device(D.data_ptr(), G.data_ptr())
+        if world > 1:
+            parallel.allreduce_device(G)
+
+    step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    tm, stt = b.timings(), b.stats()
+    b.close()
+    return {"workload": WORKLOADS[workload][0], "n_basis": n, "storage": storage, "screening": screen, "ms_per_step": ms,
+            "shell_quartets_per_s": nq / (ms * 1e-3), "shell_quartets_unique": nq, "shell_quartets_evaluated": stt["shell_quartets_evaluated"],
+            "class_kernels_ms": tm["class_kernels_ms"], "g_device_ms": tm["g_device_ms"],
+            "class_kernels_model_tflops": stt["model_flops"] / (tm["class_kernels_ms"] * 1e-3) * 1e-12 if tm["class_kernels_ms"] > 0 else None}
 
 
 def main():
@@ -371,6 +426,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--ref-budget", type=float, default=12.0, help="seconds of CPU work per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the secondary workloads reported in other_configs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -2,6 +2,7 @@
 // (device-side permutation of the primitive-pair tables), the job / warp-tile plan, kernel dispatch.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <numeric>
 
 #include "../../include/fock_b200.h"
@@ -13,6 +14,7 @@ namespace fock {
 namespace {
 
 const int kClsLA[3] = {0, 1, 1}, kClsLB[3] = {0, 0, 1};
+constexpr int kMaxSublists = 48;
 
 template <int LA, int LB, int LC, int LD, int KC0, int KCN, class Sink>
 void launch_mode(const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, cudaStream_t st) {
@@ -49,25 +51,45 @@ void launch_diag_mode(const DiagLaunch &dl, const DiagSink &sink, int mode, dim3
         eri_diag_kernel<LA, LB, false, KC0, KCN><<<grid, kClassThreads, smem, st>>>(dl, sink);
 }
 
-// sorted tables from the natural-order master: position i of a sublist takes natural pair perm[i]
-__global__ void permute_pairs_kernel(const double *__restrict__ bra_nat, const int *__restrict__ meta_nat,
-                                     const int *__restrict__ perm, int n, int K, int nf, int npad,
-                                     double *__restrict__ bra, double *__restrict__ ket, int *__restrict__ meta) {
-    const int i = blockIdx.x;
-    if (i >= n) return;
-    const int src = perm[i];
-    const int len = K * nf;
+// sorted tables from the natural-order master: position i of a sublist takes natural pair perm[i].
+// One launch for all sublists; block = one pair.
+struct PermuteDesc {
+    size_t bra_off, ket_off, meta_off;
+    int first, n, K, nf, npad;
+};
+struct PermuteTable {
+    PermuteDesc d[kMaxSublists];
+    int count;
+};
+
+__global__ void permute_pairs_kernel(PermuteTable tab, const double *__restrict__ bra_nat, const int *__restrict__ meta_nat,
+                                     const int *__restrict__ perm, double *__restrict__ bra, double *__restrict__ ket,
+                                     int *__restrict__ meta) {
+    const int g = blockIdx.x;
+    int s = 0;
+    while (s + 1 < tab.count && g >= tab.d[s + 1].first) ++s;
+    const PermuteDesc d = tab.d[s];
+    const int i = g - d.first;
+    if (i >= d.n) return;
+    const int src = perm[d.meta_off / 2 + i];
+    const int len = d.K * d.nf;
+    const double *in = bra_nat + d.bra_off + (size_t)src * len;
+    double *ob = bra + d.bra_off + (size_t)i * len, *ok = ket + d.ket_off + i;
     for (int e = threadIdx.x; e < len; e += blockDim.x) {
-        const double v = bra_nat[(size_t)src * len + e];
-        bra[(size_t)i * len + e] = v;
-        ket[(size_t)e * npad + i] = v;  // e = ij*nf + f
+        const double v = in[e];
+        ob[e] = v;
+        ok[(size_t)e * d.npad] = v;  // e = ij*nf + f
     }
-    if (threadIdx.x < 2) meta[2 * i + threadIdx.x] = meta_nat[2 * src + threadIdx.x];
+    if (threadIdx.x < 2) meta[d.meta_off + 2 * i + threadIdx.x] = meta_nat[d.meta_off + 2 * src + threadIdx.x];
 }
 
 }  // namespace
 
 int ClassEngine::upload_master(std::string &err) {
+    if ((int)sd->sublists.size() > kMaxSublists) {
+        err = "more (class, primitive-count) sublists than the class engine supports";
+        return 1;
+    }
     std::vector<double> bra, ket;
     std::vector<int> meta;
     build_pair_tables(*sd, bra, ket, meta);
@@ -78,7 +100,9 @@ int ClassEngine::upload_master(std::string &err) {
     if ((e = alloc((void **)&d_bra_nat, bra.size() * 8)) != cudaSuccess || (e = alloc((void **)&dev->d_bra, bra.size() * 8)) != cudaSuccess ||
         (e = alloc((void **)&dev->d_ket, ket.size() * 8)) != cudaSuccess || (e = alloc((void **)&d_meta_nat, meta.size() * 4)) != cudaSuccess ||
         (e = alloc((void **)&dev->d_meta, meta.size() * 4)) != cudaSuccess || (e = alloc((void **)&d_perm, meta.size() * 2 + 8)) != cudaSuccess ||
-        (e = cudaMallocHost((void **)&h_perm, meta.size() * 2 + 8)) != cudaSuccess) {
+        (e = cudaMallocHost((void **)&h_perm, meta.size() * 2 + 8)) != cudaSuccess ||
+        (e = alloc((void **)&d_maxdiag, meta.size() * 4 + 8)) != cudaSuccess ||
+        (e = cudaMallocHost((void **)&h_maxdiag, meta.size() * 4 + 8)) != cudaSuccess) {
         err = std::string("pair tables: ") + cudaGetErrorString(e);
         return 1;
     }
@@ -110,12 +134,14 @@ int ClassEngine::upload_master(std::string &err) {
 // Diagonal pass: every class pair's (AB|AB) block from the natural-order tables; only (xy|xy) kept.
 int ClassEngine::run_diagonal(double *d_diag, std::string &err) {
     int launches = 0;
-    const DiagSink sink{d_diag};
+    const size_t npairs = dev->meta_ints / 2;
+    cudaMemsetAsync(d_maxdiag, 0, npairs * sizeof(unsigned long long), stream);
+    const DiagSink sink{d_diag, d_maxdiag};
     for (size_t si = 0; si < sd->sublists.size(); ++si) {
         const Sublist &s = sd->sublists[si];
         const int n = (int)s.pair_ids.size();
         if (!n) continue;
-        DiagLaunch dl{d_bra_nat + s.bra_off, d_meta_nat + s.meta_off, dev->d_shell_bf, boys_poly, boys_ni, s.K, n};
+        DiagLaunch dl{d_bra_nat + s.bra_off, d_meta_nat + s.meta_off, dev->d_shell_bf, boys_poly, boys_ni, s.K, n, (int)(s.meta_off / 2)};
         dim3 grid((unsigned)std::min((n + kClassWarps - 1) / kClassWarps, num_sms * 4));
         if (s.cls == 0) {
             launch_diag_mode<0, 0, 0, 1>(dl, sink, mode, grid, stream);
@@ -130,6 +156,8 @@ int ClassEngine::run_diagonal(double *d_diag, std::string &err) {
             launches += 3;
         }
     }
+    // per-pair maxima to the pinned host image (the only thing the host needs from the diagonal pass)
+    cudaMemcpyAsync(h_maxdiag, d_maxdiag, npairs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         err = std::string("diagonal kernels: ") + cudaGetErrorString(e);
@@ -140,59 +168,65 @@ int ClassEngine::run_diagonal(double *d_diag, std::string &err) {
 
 // With the diagonal on the host: per-pair max |(xy|xy)|, sort each sublist (descending), permute the
 // device tables accordingly.
-int ClassEngine::sort_by_diagonal(const double *h_diag, std::string &err) {
-    for (ShellPair &p : sd->pairs) {
-        const Shell &A = sd->shells[p.A], &B = sd->shells[p.B];
-        double m = 0.0;
-        for (int ca = 0; ca < ncart(A.L); ++ca)
-            for (int cb = 0; cb < ncart(B.L); ++cb) {
-                const int x = A.bf[ca], y = B.bf[cb];
-                if (x < 0 || y < 0) continue;
-                const double d = std::fabs(h_diag[x >= y ? tri(x, y) : tri(y, x)]);
-                if (std::isnan(d)) m = INFINITY; else if (d > m) m = d;
-            }
-        p.maxdiag = m;
-    }
+int ClassEngine::sort_by_diagonal(std::string &err) {
     int *perm = h_perm;  // pinned; one entry per class pair
-    int launches = 0;
+    const double *maxd = reinterpret_cast<const double *>(h_maxdiag);  // natural order, by sublist
+    PermuteTable tab{};
+    int first = 0;
+    // keys: bit patterns of the non-negative maxima order like the doubles themselves; complemented
+    // for a descending sort, index as tie-break (deterministic)
+    struct Key {
+        unsigned long long k;
+        int i;
+        bool operator<(const Key &o) const { return k != o.k ? k < o.k : i < o.i; }
+    };
+    std::vector<Key> keyed;
     for (size_t si = 0; si < sd->sublists.size(); ++si) {
         Sublist &s = sd->sublists[si];
         const std::vector<int> &nat = nat_ids[si];
         const int n = (int)nat.size();
-        std::vector<std::pair<double, int>> keyed(n);  // contiguous keys: cache-friendly sort
-        for (int i = 0; i < n; ++i) keyed[i] = std::make_pair(-sd->pairs[nat[i]].maxdiag, i);
-        std::sort(keyed.begin(), keyed.end());  // descending maxdiag, ties by natural index (deterministic)
+        const double *m = maxd + s.meta_off / 2;
+        keyed.resize(n);  // contiguous keys: cache-friendly sort
+        const unsigned long long *mb = h_maxdiag + s.meta_off / 2;
         for (int i = 0; i < n; ++i) {
-            s.pair_ids[i] = nat[keyed[i].second];
-            perm[s.meta_off / 2 + i] = keyed[i].second;
+            sd->pairs[nat[i]].maxdiag = m[i];
+            keyed[i] = Key{~mb[i], i};
+        }
+        std::sort(keyed.begin(), keyed.end());
+        for (int i = 0; i < n; ++i) {
+            s.pair_ids[i] = nat[keyed[i].i];
+            perm[s.meta_off / 2 + i] = keyed[i].i;
+        }
+        if (n > 0 && tab.count < kMaxSublists) {
+            tab.d[tab.count++] = PermuteDesc{s.bra_off, s.ket_off, s.meta_off, first, n, s.K, s.nf, s.npad};
+            first += n;
         }
     }
     cudaMemcpyAsync(d_perm, perm, (dev->meta_ints / 2) * sizeof(int), cudaMemcpyHostToDevice, stream);
-    for (const Sublist &s : sd->sublists) {
-        const int n = (int)s.pair_ids.size();
-        if (!n) continue;
-        permute_pairs_kernel<<<n, 64, 0, stream>>>(d_bra_nat + s.bra_off, d_meta_nat + s.meta_off, d_perm + s.meta_off / 2, n, s.K, s.nf,
-                                                   s.npad, dev->d_bra + s.bra_off, dev->d_ket + s.ket_off, dev->d_meta + s.meta_off);
-        ++launches;
-    }
+    if (first > 0)
+        permute_pairs_kernel<<<first, 64, 0, stream>>>(tab, d_bra_nat, d_meta_nat, d_perm, dev->d_bra, dev->d_ket, dev->d_meta);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         err = std::string("permute pair tables: ") + cudaGetErrorString(e);
         return -1;
     }
     plan_valid = false;
-    return launches;
+    return 1;
 }
 
 // Number of ket pairs (sorted descending by maxdiag) that pass the shell-level bound against a bra
 // pair with value db.  The basis-function rule sqrt(d1*d2) > thr is monotone in both arguments, so
 // when the bound on the per-pair maxima fails every component fails.
+// (The shell-level bound only has to be conservative -- the exact rule is re-applied per integral in
+// the sink -- so it compares the product with thr^2 shrunk by a few ulps instead of taking a sqrt.)
+static inline bool pair_bound_passes(double db, double dk, double thr2_slack) { return db * dk > thr2_slack; }
 static int surviving_prefix(double db, const std::vector<double> &dk, int screen, double thr) {
     if (screen == FOCK_SCREEN_OFF) return (int)dk.size();
+    const double t2 = thr * thr * (1.0 - 1e-12);
     int lo = 0, hi = (int)dk.size();  // first index that fails
     while (lo < hi) {
         const int mid = (lo + hi) / 2;
-        if (std::sqrt(db * dk[mid]) > thr) lo = mid + 1; else hi = mid;
+        if (pair_bound_passes(db, dk[mid], t2)) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -258,18 +292,21 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
                     table.resize(off + (size_t)nb + 1);
                     long long *prefix = table.data() + off;
                     long long quartets = 0;
+                    const double *mdb = md[b].data(), *mdk = md[k].data();
+                    const double thr2_slack = thr * thr * (1.0 - 1e-12);
                     // ncols(r) is non-increasing in r (both lists sorted descending): walk it down
                     int nc = (screen == FOCK_SCREEN_OFF) ? nk : surviving_prefix(md[b][0], md[k], screen, thr);
                     for (int r = 0; r < nb; ++r) {
                         if (screen != FOCK_SCREEN_OFF)
-                            while (nc > 0 && !(std::sqrt(md[b][r] * md[k][nc - 1]) > thr)) --nc;
+                            while (nc > 0 && !pair_bound_passes(mdb[r], mdk[nc - 1], thr2_slack)) --nc;
                         prefix[r] = quartets;
                         quartets += (b == k) ? std::min(nc, r + 1) : nc;
                     }
                     prefix[nb] = quartets;
                     // K-split: keep one thread's loop below ~6000 instructions (class cost x depth)
+                    static const int kSplitMax = getenv("FOCK_KSPLIT_MAX") ? atoi(getenv("FOCK_KSPLIT_MAX")) : 32;
                     int S = 1;
-                    while (S < 32 && 2 * S <= sk.K && (double)sb.K * sk.K * kCost[cb][ck] / S > loop_limit) S *= 2;
+                    while (S < kSplitMax && 2 * S <= sk.K && (double)sb.K * sk.K * kCost[cb][ck] / S > loop_limit) S *= 2;
                     const long long per_tile = 32 / S;
                     const long long tiles = (quartets + per_tile - 1) / per_tile;
                     plan_stats.shell_quartets_total += (b == k) ? (long long)nb * (nb + 1) / 2 : (long long)nb * nk;
@@ -365,6 +402,8 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
             cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming);
         }
     }
+    static const int kStreams = getenv("FOCK_STREAMS") ? std::max(1, std::min(kAuxStreams, atoi(getenv("FOCK_STREAMS")))) : kAuxStreams;
+    static const int kBlocksPerSm = getenv("FOCK_BLOCKS_PER_SM") ? atoi(getenv("FOCK_BLOCKS_PER_SM")) : 8;
     cudaEventRecord(ev_fork, stream);
     for (int i = 0; i < kAuxStreams; ++i) cudaStreamWaitEvent(aux[i], ev_fork, 0);
     int slot = 0;
@@ -382,8 +421,8 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
         const long long mine = (pl.total_tiles - plan_rank + plan_world - 1) / plan_world;  // warp tiles of this rank
         if (mine <= 0) continue;
         // persistent blocks: enough to fill the machine, each strides over the warp tiles
-        dim3 grid((unsigned)std::min<long long>((mine + kClassWarps - 1) / kClassWarps, (long long)num_sms * 8));
-        launches += launch_class(pl.cb, pl.ck, cl, sink, mode, grid, aux[slot % kAuxStreams]);
+        dim3 grid((unsigned)std::min<long long>((mine + kClassWarps - 1) / kClassWarps, (long long)num_sms * kBlocksPerSm));
+        launches += launch_class(pl.cb, pl.ck, cl, sink, mode, grid, aux[slot % kStreams]);
         ++slot;
     }
     for (int i = 0; i < kAuxStreams; ++i) {
@@ -408,6 +447,8 @@ ClassEngine::~ClassEngine() {
     if (d_meta_nat) cudaFree(d_meta_nat);
     if (d_perm) cudaFree(d_perm);
     if (h_perm) cudaFreeHost(h_perm);
+    if (d_maxdiag) cudaFree(d_maxdiag);
+    if (h_maxdiag) cudaFreeHost(h_maxdiag);
     if (h_table) cudaFreeHost(h_table);
     if (h_jobs) cudaFreeHost(h_jobs);
     if (ev_fork) {

@@ -42,6 +42,7 @@ struct ClassEngine {
     double *d_bra_nat = nullptr;
     int *d_meta_nat = nullptr;
     int *d_perm = nullptr;
+    unsigned long long *d_maxdiag = nullptr, *h_maxdiag = nullptr;  // per class pair, natural order (device / pinned)
     std::vector<std::vector<int>> nat_ids;  // per sublist: pair ids in natural order
 
     // plan (jobs + tile tables) of the current sorted order / screening
@@ -66,7 +67,7 @@ struct ClassEngine {
 
     int upload_master(std::string &err);                 // once, after build_pairs
     int run_diagonal(double *d_diag, std::string &err);  // returns launches or -1
-    int sort_by_diagonal(const double *h_diag, std::string &err);  // returns launches or -1
+    int sort_by_diagonal(std::string &err);  // uses h_maxdiag; returns launches or -1
     int make_plan(int screen, double thr, int rank, int world, std::string &err);
     template <class Sink>
     int run_plan(const Sink &sink, std::string &err);  // returns launches or -1

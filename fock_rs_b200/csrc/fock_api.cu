@@ -279,7 +279,6 @@ static int diagonal_launch(fock_ctx *ctx, int *launches) {
     cudaStream_t st = ctx->stream;
     const int T = 128;
     std::string err;
-    if (!cs->h_diag) FOCK_CUDA_TRY(ctx, cudaMallocHost((void **)&cs->h_diag, ctx->npair * sizeof(double)));
     if (!cs->ev_diag) FOCK_CUDA_TRY(ctx, cudaEventCreateWithFlags(&cs->ev_diag, cudaEventDisableTiming));
     if (!cs->ev_k0) FOCK_CUDA_TRY(ctx, cudaEventCreate(&cs->ev_k0));
     if (!cs->ev_k1) FOCK_CUDA_TRY(ctx, cudaEventCreate(&cs->ev_k1));
@@ -298,8 +297,7 @@ static int diagonal_launch(fock_ctx *ctx, int *launches) {
         *launches += 1;
     }
     FOCK_CUDA_TRY(ctx, cudaGetLastError());
-    FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(cs->h_diag, ctx->d_diag, ctx->npair * sizeof(double), cudaMemcpyDeviceToHost, st));
-    FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_diag, st));
+    FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_diag, st));  // after the copy of the per-pair maxima queued by run_diagonal
     return FOCK_OK;
 }
 
@@ -309,7 +307,7 @@ static int diagonal_finish(fock_ctx *ctx, int *launches) {
     if (!ctx->shells.pairs.empty()) {
         const auto t0 = std::chrono::steady_clock::now();
         std::string err;
-        const int l = cs->engine.sort_by_diagonal(cs->h_diag, err);
+        const int l = cs->engine.sort_by_diagonal(err);
         if (l < 0) {
             ctx->err = err;
             return FOCK_ERR_CUDA;

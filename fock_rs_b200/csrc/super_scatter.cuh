@@ -49,9 +49,18 @@ __device__ __forceinline__ void for_each_super_target(int i, int j, int k, int l
     const CanonQuartet key = canon_quartet(i, j, k, l);
     f(key.ab, key.cd, v);
     const CanonQuartet t1 = canon_quartet(key.a, key.c, key.b, key.d);
+    const CanonQuartet t2 = canon_quartet(key.a, key.d, key.b, key.c);
+    // Fast path (the overwhelmingly common case in anything but tiny molecules): four distinct
+    // functions.  Then (ac|bd) and (ad|bc) are two different slots, each containing the integral in
+    // exactly one of its two exchange terms.
+    if (key.a != key.b && key.c != key.d && key.a != key.c && key.a != key.d && key.b != key.c && key.b != key.d) {
+        const double x = -0.25 * v;
+        f(t1.ab, t1.cd, x);
+        f(t2.ab, t2.cd, x);
+        return;
+    }
     const double c1 = exchange_coefficient(t1, key);
     if (c1 != 0.0) f(t1.ab, t1.cd, c1 * v);
-    const CanonQuartet t2 = canon_quartet(key.a, key.d, key.b, key.c);
     if (!t2.same(t1)) {
         const double c2 = exchange_coefficient(t2, key);
         if (c2 != 0.0) f(t2.ab, t2.cd, c2 * v);
