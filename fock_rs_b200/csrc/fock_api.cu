@@ -10,6 +10,7 @@
 #include "class_launch.h"
 #include "context.h"
 #include "eri_class.cuh"
+#include "sq_launch.cuh"
 #include "tensor_kernels.cuh"
 
 using namespace fock;
@@ -42,7 +43,10 @@ void make_boys_table(std::vector<double> &tab) {
 struct ClassState {
     ClassEngine engine;
     ClassStats stats;
-    unsigned char *d_bf_class_ok = nullptr;
+    unsigned char *d_bf_class_ok = nullptr;  // function sits in an s/p class shell
+    unsigned char *d_bf_covered = nullptr;   // function is handled by a shell-level path (class or shell-quartet kernel)
+    bool all_covered = false;
+    SqState sq;
     unsigned long long *d_counter = nullptr;
     double *d_boys_poly = nullptr;
     double *h_diag = nullptr;  // pinned image of d_diag
@@ -219,10 +223,22 @@ int fock_create(const fock_basis *b, const fock_opts *opts_in, fock_ctx **out) {
             ctx->err = err;
             return FOCK_ERR_CUDA;
         }
-        std::vector<unsigned char> ok(n);
-        for (int i = 0; i < n; ++i) ok[i] = ctx->shells.shells[ctx->shells.bf_shell[i]].class_ok ? 1 : 0;
+        std::vector<unsigned char> ok(n), covered(n);
+        if (o.kernel != 1 && cs->sq.init(ctx->shells, err)) {
+            ctx->err = err;
+            return FOCK_ERR_CUDA;
+        }
+        cs->all_covered = true;
+        for (int i = 0; i < n; ++i) {
+            const Shell &sh = ctx->shells.shells[ctx->shells.bf_shell[i]];
+            ok[i] = sh.class_ok ? 1 : 0;
+            covered[i] = (o.kernel != 1 && sh.L <= 2) ? 1 : 0;
+            if (!covered[i]) cs->all_covered = false;
+        }
         FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&cs->d_bf_class_ok, n));
         FOCK_CUDA_TRY(ctx, cudaMemcpy(cs->d_bf_class_ok, ok.data(), n, cudaMemcpyHostToDevice));
+        FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&cs->d_bf_covered, n));
+        FOCK_CUDA_TRY(ctx, cudaMemcpy(cs->d_bf_covered, covered.data(), n, cudaMemcpyHostToDevice));
         FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&cs->d_counter, sizeof(unsigned long long)));
         ctx->digest_begin = 0;
         ctx->digest_end = prow(ctx->npair);
@@ -249,7 +265,8 @@ void fock_destroy(fock_ctx *c) {
     void *ptrs[] = {ctx->d_center, ctx->d_angular, ctx->d_primoff, ctx->d_exp,  ctx->d_coef, ctx->d_boys_lut,
                     ctx->d_boys_tab, ctx->d_diag,   ctx->d_V,       ctx->d_P,    ctx->d_dvec, ctx->d_yvec,
                     ctx->d_D,      ctx->d_G,       ctx->pairs.d_bra, ctx->pairs.d_ket, ctx->pairs.d_meta,
-                    ctx->pairs.d_shell_bf, ctx->pairs.d_maxdiag, ctx->cs.d_bf_class_ok, ctx->cs.d_counter, ctx->cs.d_boys_poly};
+                    ctx->pairs.d_shell_bf, ctx->pairs.d_maxdiag, ctx->cs.d_bf_class_ok, ctx->cs.d_bf_covered, ctx->cs.d_counter, ctx->cs.d_boys_poly};
+    ctx->cs.sq.destroy();
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -296,8 +313,9 @@ static int diagonal_launch(fock_ctx *ctx, int *launches) {
                                                                               cs->d_bf_class_ok, 1, ctx->npair, ctx->d_diag);
         *launches += 1;
     }
+    cs->sq.launch_pairmax(ctx->d_diag, st);
     FOCK_CUDA_TRY(ctx, cudaGetLastError());
-    FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_diag, st));  // after the copy of the per-pair maxima queued by run_diagonal
+    FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_diag, st));  // after the copies of the per-pair maxima
     return FOCK_OK;
 }
 
@@ -391,9 +409,16 @@ int fock_eri_build(fock_ctx *ctx) {
             ctx->stats[8] = (int64_t)cs->stats.model_flops;
             ctx->stats[10] = cs->stats.warp_tiles;
         }
-        if (!ctx->shells.all_class_ok) {
+        if (cs->sq.enabled) {  // shell quartets with d shells / irregular shells
+            cs->sq.prepare(ctx->shells, ctx->opts.screen, thr, ctx->boys(), ctx->opts.mode, b_rank, b_world, st);
+            TensorSink sink{Vp, Pp, ctx->d_diag, thr, ctx->opts.screen};
+            launches += cs->sq.run(sink, cs->engine.num_sms, st);
+            ctx->stats[4] += cs->sq.quartets;
+            ctx->stats[11] = cs->sq.quartets;
+        }
+        if (!cs->all_covered) {  // functions above d: per-function generic kernel
             generic_tensor_kernel<<<(unsigned)((ctx->nelem + T - 1) / T), T, 0, st>>>(
-                ctx->basis_dev(), ctx->boys(), ctx->opts.mode, cs->d_bf_class_ok, 1, ctx->opts.screen, thr, ctx->d_diag,
+                ctx->basis_dev(), ctx->boys(), ctx->opts.mode, cs->d_bf_covered, 1, ctx->opts.screen, thr, ctx->d_diag,
                 ctx->nelem, b_rank, b_world, Vp, Pp, cs->d_counter);
             launches += 1;
         }
@@ -590,10 +615,17 @@ int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev) {
             ctx->stats[8] = (int64_t)cs->stats.model_flops;
             ctx->stats[10] = cs->stats.warp_tiles;
         }
-        if (!ctx->shells.all_class_ok) {
+        if (cs->sq.enabled) {
+            cs->sq.prepare(ctx->shells, ctx->opts.screen, thr, ctx->boys(), ctx->opts.mode, ctx->opts.rank, ctx->opts.world, st);
+            DirectSink sink{ctx->d_yvec, ctx->d_dvec, ctx->d_diag, thr, ctx->opts.screen};
+            launches += cs->sq.run(sink, cs->engine.num_sms, st);
+            ctx->stats[4] += cs->sq.quartets;
+            ctx->stats[11] = cs->sq.quartets;
+        }
+        if (!cs->all_covered) {
             const size_t mine = (ctx->nelem + ctx->opts.world - 1) / ctx->opts.world;
             generic_direct_kernel<<<(unsigned)((mine + 127) / 128), 128, 0, st>>>(
-                ctx->basis_dev(), ctx->boys(), ctx->opts.mode, cs->d_bf_class_ok, 1, ctx->opts.screen, thr, ctx->d_diag, ctx->nelem,
+                ctx->basis_dev(), ctx->boys(), ctx->opts.mode, cs->d_bf_covered, 1, ctx->opts.screen, thr, ctx->d_diag, ctx->nelem,
                 ctx->opts.rank, ctx->opts.world, ctx->d_dvec, ctx->d_yvec);
             launches += 1;
         }

@@ -45,12 +45,26 @@ bool build_shells(int n, const double *center, const int32_t *angular, const int
             bool ok = s.L == L && s.nprim == np && s.bf[comp] < 0;
             for (int k = 0; ok && k < 3; ++k) ok = same_bits(s.c[k], center[3 * f + k]);
             for (int i = 0; ok && i < np; ++i) ok = same_bits(out.exps[s.prim_begin + i], fe[i]);
-            // class kernels assume one radial coefficient list per shell: components must carry
-            // bitwise-identical coefficients (true for s and p shells from BasisSet::get; d
-            // components differ by the sqrt(3) norm ratio and stay separate for now)
-            for (int i = 0; ok && i < np; ++i) ok = same_bits(out.coefs[s.prim_begin + i], fc[i]);
+            // one radial coefficient list per shell: a component may differ from it by a constant factor
+            // (Cartesian d components differ by the sqrt(3) norm ratio, basis/src/primitives.rs:19-27);
+            // the ratio must be the same for every primitive to within a few ulps
+            double ratio = 1.0;
+            if (ok) {
+                const double r0 = out.coefs[s.prim_begin];
+                ok = r0 != 0.0 && std::isfinite(fc[0] / r0);
+                if (ok) ratio = fc[0] / r0;
+                for (int i = 0; ok && i < np; ++i) {
+                    const double want = ratio * out.coefs[s.prim_begin + i];
+                    ok = std::fabs(fc[i] - want) <= 8e-16 * std::fabs(want);
+                }
+                bool identical = true;
+                for (int i = 0; identical && i < np; ++i) identical = same_bits(out.coefs[s.prim_begin + i], fc[i]);
+                if (identical) ratio = 1.0;
+            }
             if (ok) {
                 s.bf[comp] = f;
+                s.scale[comp] = ratio;
+                if (ratio != 1.0) s.class_ok = false;
                 out.bf_shell[f] = cur;
                 out.bf_comp[f] = comp;
                 joined = true;

@@ -32,6 +32,7 @@ struct Shell {
     int nprim = 0;
     int prim_begin = 0;  // into ShellData::exps / coefs (radial coefficients, norm of component 0 folded in)
     int bf[6] = {-1, -1, -1, -1, -1, -1};  // basis-function index of each Cartesian component (-1 = absent)
+    double scale[6] = {1, 1, 1, 1, 1, 1};  // coefficient list of component c = scale[c] * radial list
     bool class_ok = false;  // eligible for the class kernels (L <= kMaxClassL, unit component scales)
 };
 

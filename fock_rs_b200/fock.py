@@ -162,7 +162,7 @@ class FockBuilder:
         return {
             "n_basis": s[0], "shells": s[1], "shell_pairs": s[2], "shell_quartets_unique": s[3],
             "shell_quartets_evaluated": s[4], "prim_quartets_evaluated": s[5], "launches_build": s[6],
-            "launches_g": s[7], "model_flops": s[8], "generic_integrals_evaluated": s[9], "warp_tiles": s[10],
+            "launches_g": s[7], "model_flops": s[8], "generic_integrals_evaluated": s[9], "warp_tiles": s[10], "general_shell_quartets_evaluated": s[11],
         }
 
 

@@ -155,7 +155,9 @@ int fock_timings(fock_ctx *ctx, double *ms, int32_t n);
 /* Counters: [0] N  [1] shells  [2] shell pairs  [3] unique shell quartets (unscreened)
  *   [4] shell quartets evaluated by the last build / direct G  [5] primitive quartets evaluated
  *   [6] kernel launches of the last fock_eri_build  [7] kernel launches of the last fock_build_g
- *   [8] model FP64 flops of the quartets evaluated (SURVEY.md section 8d formula) */
+ *   [8] model FP64 flops of the class quartets evaluated (SURVEY.md section 8d formula)
+ *   [9] integrals evaluated by the per-function generic kernel  [10] warp tiles of the class launches
+ *   [11] shell quartets evaluated by the general (d-capable) shell-quartet kernel */
 int fock_stats(fock_ctx *ctx, int64_t *out, int32_t n);
 
 /* Measurement aid (no reference counterpart): sustained FP64 FMA rate of this GPU from a

@@ -277,3 +277,35 @@ def test_device_boys_function_matches_reference(mode, exact):
         with pytest.raises(_lib.FockError) as ei:
             b.boys(t[:4], 11)
         assert ei.value.code == _lib.ERR_BOYS_ORDER
+
+
+@pytest.mark.parametrize("mode,oflags", MODES)
+@pytest.mark.parametrize("mol,basis", [("water", "6-31G**"), ("ethene", "6-31G**")])
+def test_d_shell_quartets_through_shell_quartet_kernel(mol, basis, mode, oflags):
+    """Cartesian d shells (total L up to 8, Boys order up to 8) go through the general shell-quartet
+    kernel; tensor, G (in-core and direct) against the oracle."""
+    fb = flat_for(mol, basis)
+    ob = oracle.OracleBasis.from_flat(fb)
+    want, _ = oracle.from_basis_packed(ob, oflags, fast=True)
+    D = random_symmetric_density(fb.n_basis, seed=12)
+    with FockBuilder(fb, mode=mode) as b:
+        b.eri_build()
+        got = b.eri_export_packed()
+        G = b.build_g(D)
+        st = b.stats()
+    assert st["general_shell_quartets_evaluated"] > 0 and st["generic_integrals_evaluated"] == 0
+    assert np.max(np.abs(got - want)) <= ERI_TOL
+    assert_same_cut(got, want)
+    G_want = oracle.build_g(want, fb.n_basis, D)
+    assert np.max(np.abs(G - G_want)) <= G_TOL
+    with FockBuilder(fb, mode=mode, storage=_lib.STORAGE_DIRECT) as b:
+        Gd = b.eri_build().build_g(D)
+    assert np.max(np.abs(Gd - G_want)) <= G_TOL
+
+
+def test_scf_with_d_shells_water_631gss():
+    atoms = atoms_for("water", "6-31G**")
+    r = try_scf(atoms, 100, 1e-6, 0, engine=FockEngine())
+    ro = try_scf(atoms, 100, 1e-6, 0, engine=OracleEngine(oracle.FAITHFUL, fast=True))
+    assert r is not None and ro is not None and r.iterations == ro.iterations
+    assert abs(r.total_energy - ro.total_energy) <= E_TOL
