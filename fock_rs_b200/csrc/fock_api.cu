@@ -1,5 +1,6 @@
 // fock_api.cu -- implementation of the C ABI in include/fock_b200.h.
 #include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -384,6 +385,7 @@ int fock_eri_build(fock_ctx *ctx) {
         FOCK_TRY(diagonal_finish(ctx, &launches));  // host sorting overlaps the memsets above
         const double thr = screen_threshold(ctx->opts);
         double *Vp = want_v ? ctx->d_V : nullptr, *Pp = gather ? nullptr : ctx->d_P;
+        if (getenv("FOCK_NULL_SINK")) Vp = Pp = nullptr;  // measurement aid: integrals are computed and dropped
         // In-core builds are REPLICATED across ranks (every rank forms the whole supermatrix, ~ms);
         // what is sharded is the per-iteration streaming of it (fock_set_digest_range).  Sharding the
         // build instead would need a reduce-scatter of the full packed tensor (1.9 GB at N=208, more
