@@ -229,7 +229,8 @@ def config_dict(args, flat):
         "mode": args.mode,
         "screening": "reference 1e-6 cut (basis/src/electron_tensor.rs:134-155)" if args.screen == "ref" else "off",
         "l2": "inputs larger than L2 (packed tensor) " if flat.n_basis >= 150 else "L2 flushed between timed steps (256 MiB write)",
-        "parallelism": f"shell-quartet tiles sharded over {args.gpus} rank(s); one all-reduce of G per step",
+        "parallelism": (f"shell-quartet tiles sharded over {args.gpus} rank(s); one all-reduce of G per step"
+                        + ("" if args.gpus == 1 or args.storage != "incore" else f"; in-core sharding = {args.incore_shard}")),
     }
 
 
@@ -255,7 +256,8 @@ def run_ours(args):
     mode = _lib.MODE_FAITHFUL if args.mode == "faithful" else _lib.MODE_ACCURATE
     screen = _lib.SCREEN_REFERENCE if args.screen == "ref" else _lib.SCREEN_OFF
     storage = _lib.STORAGE_INCORE if args.storage == "incore" else _lib.STORAGE_DIRECT
-    b = FockBuilder(flat, mode=mode, screen=screen, storage=storage, device=local, rank=rank, world=world, keep_eri=False)
+    b = FockBuilder(flat, mode=mode, screen=screen, storage=storage, device=local, rank=rank, world=world, keep_eri=False,
+                    incore_shard=1 if args.incore_shard == "build" else 0)
     stream = torch.cuda.current_stream()
     b.set_stream(stream.cuda_stream)
     rng = np.random.default_rng(20261017)
@@ -436,6 +438,8 @@ def main():
     ap.add_argument("--mode", default="faithful", choices=["faithful", "accurate"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--ref-budget", type=float, default=12.0, help="seconds of CPU work per step of --impl reference")
+    ap.add_argument("--incore-shard", default="build", choices=["build", "digest"],
+                    help="N>1, in-core: shard the build (default: the step is 1 build + 1 G build) or replicate it and shard the digestion")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the secondary workloads reported in other_configs")
     args = ap.parse_args()

@@ -56,6 +56,7 @@ class COpts(C.Structure):
         ("world", C.c_int32),
         ("keep_eri", C.c_int32),
         ("kernel", C.c_int32),
+        ("incore_shard", C.c_int32),
     ]
 
 

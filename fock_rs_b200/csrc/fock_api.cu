@@ -96,6 +96,7 @@ void fock_default_opts(fock_opts *o) {
     o->world = 1;
     o->keep_eri = 1;
     o->kernel = 0;
+    o->incore_shard = 0;
 }
 
 size_t fock_packed_len(int32_t n) {
@@ -124,6 +125,10 @@ int fock_create(const fock_basis *b, const fock_opts *opts_in, fock_ctx **out) {
         return FOCK_ERR_BAD_ARG;
     }
     const int n = b->n_basis;
+    if (n > 65535) {
+        g_create_error = "more than 65535 basis functions are not supported (32-bit pair indices)";
+        return FOCK_ERR_UNSUPPORTED;
+    }
     for (int i = 0; i < n; ++i) {
         const int l = b->angular[3 * i] + b->angular[3 * i + 1] + b->angular[3 * i + 2];
         if (b->angular[3 * i] < 0 || b->angular[3 * i + 1] < 0 || b->angular[3 * i + 2] < 0 ||
@@ -390,7 +395,8 @@ int fock_eri_build(fock_ctx *ctx) {
         // what is sharded is the per-iteration streaming of it (fock_set_digest_range).  Sharding the
         // build instead would need a reduce-scatter of the full packed tensor (1.9 GB at N=208, more
         // than the build itself costs).  The integral-direct path shards the quartet tiles.
-        const int b_rank = 0, b_world = 1;
+        const bool shard_build = ctx->opts.incore_shard == 1 && ctx->opts.world > 1;
+        const int b_rank = shard_build ? ctx->opts.rank : 0, b_world = shard_build ? ctx->opts.world : 1;
         diag_to_tensor_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(ctx->d_diag, ctx->npair, b_rank, b_world, Vp, Pp);
         launches += 1;
         if (!ctx->shells.pairs.empty()) {
@@ -451,7 +457,7 @@ int fock_eri_build(fock_ctx *ctx) {
         ctx->timings[0] = ms;
         ctx->timings[1] = ctx->timings[2] = 0;
     }
-    if (ctx->opts.storage == FOCK_STORAGE_INCORE && ctx->opts.world > 1) {
+    if (ctx->opts.storage == FOCK_STORAGE_INCORE && ctx->opts.world > 1 && ctx->opts.incore_shard != 1) {
         // default sharding of the digestion: equal contiguous element ranges of the packed supermatrix
         const size_t total = prow(ctx->npair);
         const size_t chunk = ((total + ctx->opts.world - 1) / ctx->opts.world + 3) / 4 * 4;  // whole 32-byte sectors

@@ -26,8 +26,9 @@ __device__ __forceinline__ CanonQuartet canon_quartet(int i, int j, int k, int l
     q.b = i >= j ? j : i;
     q.c = k >= l ? k : l;
     q.d = k >= l ? l : k;
-    q.ab = tri((size_t)q.a, (size_t)q.b);
-    q.cd = tri((size_t)q.c, (size_t)q.d);
+    // 32-bit triangular indices (N <= 65535 functions), widened afterwards
+    q.ab = (unsigned)q.a * ((unsigned)q.a + 1u) / 2u + (unsigned)q.b;
+    q.cd = (unsigned)q.c * ((unsigned)q.c + 1u) / 2u + (unsigned)q.d;
     if (q.ab < q.cd) {
         int t = q.a; q.a = q.c; q.c = t;
         t = q.b; q.b = q.d; q.d = t;

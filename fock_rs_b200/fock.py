@@ -36,7 +36,7 @@ class FockBuilder:
     """Owns one `fock_ctx`.  Options mirror `fock_opts` (include/fock_b200.h)."""
 
     def __init__(self, basis, mode=_lib.MODE_FAITHFUL, screen=_lib.SCREEN_REFERENCE, tau=1e-6, storage=_lib.STORAGE_INCORE,
-                 device=-1, rank=0, world=1, keep_eri=True, kernel=0):
+                 device=-1, rank=0, world=1, keep_eri=True, kernel=0, incore_shard=0):
         self._L = _lib.load()
         self._ctx = C.c_void_p()
         flat = _as_flat(basis)
@@ -53,6 +53,7 @@ class FockBuilder:
         self._L.fock_default_opts(C.byref(opts))
         opts.mode, opts.screen, opts.tau, opts.storage = int(mode), int(screen), float(tau), int(storage)
         opts.device, opts.rank, opts.world, opts.keep_eri, opts.kernel = int(device), int(rank), int(world), int(bool(keep_eri)), int(kernel)
+        opts.incore_shard = int(incore_shard)
         self.opts = opts
         st = self._L.fock_create(C.byref(cb), C.byref(opts), C.byref(self._ctx))
         if st != _lib.OK:

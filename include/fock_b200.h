@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FOCK_B200_ABI_VERSION 1
+#define FOCK_B200_ABI_VERSION 2
 
 typedef struct fock_ctx fock_ctx;
 
@@ -82,6 +82,9 @@ typedef struct {
     int32_t world;    /* number of shards (1 = whole job) */
     int32_t keep_eri; /* in-core: also keep the raw (ij|kl) tensor for fock_eri_get/export (default 1) */
     int32_t kernel;   /* 0 = class kernels (default), 1 = force the generic per-function kernel */
+    int32_t incore_shard; /* world > 1, in-core: 0 = replicate the build, shard the per-iteration streaming
+                             (best when a build is followed by more than ~T_build/T_G iterations);
+                             1 = shard the build, every rank streams its own partial supermatrix */
 } fock_opts;
 
 void fock_default_opts(fock_opts *opts);
@@ -137,10 +140,12 @@ int fock_one_electron(fock_ctx *ctx, int32_t n_nuclei, const double *nuclei_pos,
 int fock_set_stream(fock_ctx *ctx, void *cuda_stream);
 
 /* Multi-process plumbing (one process per GPU, `rank`/`world` in fock_opts).  Integral-direct
- * mode shards the shell-quartet tiles over ranks.  In-core mode replicates the (one-off) build and
- * shards the per-iteration streaming: after fock_eri_build rank r streams the r-th of `world`
+ * mode shards the shell-quartet tiles over ranks.  In-core mode by default replicates the (one-off)
+ * build and shards the per-iteration streaming: after fock_eri_build rank r streams the r-th of `world`
  * equal contiguous element ranges of the packed supermatrix; fock_set_digest_range overrides that
- * range, fock_supermatrix_device exposes the buffer and its length (rows padded to 4 doubles).  Either way
+ * range, fock_supermatrix_device exposes the buffer and its length (rows padded to 4 doubles).  With
+ * opts.incore_shard = 1 the build is sharded instead (tiles dealt to ranks) and each rank streams its
+ * own partial supermatrix in full.  Either way
  * fock_build_g returns a PARTIAL G that the caller sums with one all-reduce of N*N doubles. */
 int fock_supermatrix_device(fock_ctx *ctx, void **dev_ptr, size_t *n_elements);
 int fock_set_digest_range(fock_ctx *ctx, size_t begin, size_t end);

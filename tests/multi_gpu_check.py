@@ -33,14 +33,14 @@ def main():
         packed, _ = oracle.from_basis_packed(ob, oracle.FAITHFUL, fast=True)
         D = random_symmetric_density(n, seed=4)
         want = oracle.build_g(packed, n, D)
-        for storage in (_lib.STORAGE_INCORE, _lib.STORAGE_DIRECT):
-            with FockBuilder(fb, storage=storage, device=local, rank=rank, world=world, keep_eri=False) as b:
+        for storage, shard in ((_lib.STORAGE_INCORE, 0), (_lib.STORAGE_INCORE, 1), (_lib.STORAGE_DIRECT, 0)):
+            with FockBuilder(fb, storage=storage, device=local, rank=rank, world=world, keep_eri=False, incore_shard=shard) as b:
                 b.eri_build()
                 G = parallel.allreduce_host_matrix(b.build_g(D))
             err = float(np.max(np.abs(G - want)))
             worst = max(worst, err)
             if rank == 0:
-                print(f"{mol}/{basis} storage={storage} world={world}: max|dG| = {err:.2e}")
+                print(f"{mol}/{basis} storage={storage} incore_shard={shard} world={world}: max|dG| = {err:.2e}")
     r = try_scf(atoms_for("water", "6-31G"), 100, 1e-6, 0, engine=FockEngine(device=local))
     e_err = abs(r.total_energy - (-76.0126589918))
     if rank == 0:
