@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <numeric>
 
+#include <cub/device/device_segmented_sort.cuh>
+
 #include "../../include/fock_b200.h"
 #include "class_launch.h"
 #include "eri_class.cuh"
@@ -14,7 +16,6 @@ namespace fock {
 namespace {
 
 const int kClsLA[3] = {0, 1, 1}, kClsLB[3] = {0, 0, 1};
-constexpr int kMaxSublists = 48;
 
 template <int LA, int LB, int LC, int LD, int KC0, int KCN, class Sink>
 void launch_mode(const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, cudaStream_t st) {
@@ -53,15 +54,6 @@ void launch_diag_mode(const DiagLaunch &dl, const DiagSink &sink, int mode, dim3
 
 // sorted tables from the natural-order master: position i of a sublist takes natural pair perm[i].
 // One launch for all sublists; block = one pair.
-struct PermuteDesc {
-    size_t bra_off, ket_off, meta_off;
-    int first, n, K, nf, npad;
-};
-struct PermuteTable {
-    PermuteDesc d[kMaxSublists];
-    int count;
-};
-
 __global__ void permute_pairs_kernel(PermuteTable tab, const double *__restrict__ bra_nat, const int *__restrict__ meta_nat,
                                      const int *__restrict__ perm, double *__restrict__ bra, double *__restrict__ ket,
                                      int *__restrict__ meta) {
@@ -102,7 +94,11 @@ int ClassEngine::upload_master(std::string &err) {
         (e = alloc((void **)&dev->d_meta, meta.size() * 4)) != cudaSuccess || (e = alloc((void **)&d_perm, meta.size() * 2 + 8)) != cudaSuccess ||
         (e = cudaMallocHost((void **)&h_perm, meta.size() * 2 + 8)) != cudaSuccess ||
         (e = alloc((void **)&d_maxdiag, meta.size() * 4 + 8)) != cudaSuccess ||
-        (e = cudaMallocHost((void **)&h_maxdiag, meta.size() * 4 + 8)) != cudaSuccess) {
+        (e = cudaMallocHost((void **)&h_maxdiag, meta.size() * 4 + 8)) != cudaSuccess ||
+        (e = alloc((void **)&d_keys_sorted, meta.size() * 4 + 8)) != cudaSuccess ||
+        (e = cudaMallocHost((void **)&h_keys_sorted, meta.size() * 4 + 8)) != cudaSuccess ||
+        (e = alloc((void **)&d_iota, meta.size() * 2 + 8)) != cudaSuccess ||
+        (e = alloc((void **)&d_seg, (2 * sd->sublists.size() + 2) * sizeof(int))) != cudaSuccess) {
         err = std::string("pair tables: ") + cudaGetErrorString(e);
         return 1;
     }
@@ -127,6 +123,34 @@ int ClassEngine::upload_master(std::string &err) {
     dev->bra_doubles = bra.size();
     dev->ket_doubles = ket.size();
     dev->meta_ints = meta.size();
+    // device-side segmented sort of the per-pair maxima (one segment per sublist)
+    {
+        const int npairs = (int)(meta.size() / 2), nseg = (int)sd->sublists.size();
+        std::vector<int> iota(npairs), seg(2 * nseg);
+        permute_tab = PermuteTable{};
+        int first = 0;
+        for (int si = 0; si < nseg; ++si) {
+            const Sublist &s = sd->sublists[si];
+            const int n = (int)s.pair_ids.size(), base = (int)(s.meta_off / 2);
+            for (int i = 0; i < n; ++i) iota[base + i] = i;
+            seg[si] = base;
+            seg[nseg + si] = base + n;
+            if (n > 0) {
+                permute_tab.d[permute_tab.count++] = PermuteDesc{s.bra_off, s.ket_off, s.meta_off, first, n, s.K, s.nf, s.npad};
+                first += n;
+            }
+        }
+        permute_blocks = first;
+        cudaMemcpy(d_iota, iota.data(), iota.size() * sizeof(int), cudaMemcpyHostToDevice);
+        cudaMemcpy(d_seg, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice);
+        sort_temp_bytes = 0;
+        cub::DeviceSegmentedSort::SortPairsDescending(nullptr, sort_temp_bytes, d_maxdiag, d_keys_sorted, d_iota, d_perm, npairs, nseg,
+                                                      d_seg, d_seg + nseg, stream);
+        if ((e = cudaMalloc(&d_sort_temp, sort_temp_bytes + 16)) != cudaSuccess) {
+            err = std::string("sort scratch: ") + cudaGetErrorString(e);
+            return 1;
+        }
+    }
     plan_valid = false;
     return 0;
 }
@@ -156,7 +180,17 @@ int ClassEngine::run_diagonal(double *d_diag, std::string &err) {
             launches += 3;
         }
     }
-    // per-pair maxima to the pinned host image (the only thing the host needs from the diagonal pass)
+    // order every sublist by its pairs' maxima (descending) on the device -- non-negative doubles sort
+    // like their bit patterns -- and permute the primitive-pair tables accordingly; the host only needs
+    // the sorted maxima (for the screening prefixes) and, for the shell-quartet path, the natural ones
+    const int nseg = (int)sd->sublists.size();
+    cub::DeviceSegmentedSort::SortPairsDescending(d_sort_temp, sort_temp_bytes, d_maxdiag, d_keys_sorted, d_iota, d_perm, (int)npairs,
+                                                  nseg, d_seg, d_seg + nseg, stream);
+    if (permute_blocks > 0)
+        permute_pairs_kernel<<<permute_blocks, 64, 0, stream>>>(permute_tab, d_bra_nat, d_meta_nat, d_perm, dev->d_bra, dev->d_ket,
+                                                               dev->d_meta);
+    launches += 2;
+    cudaMemcpyAsync(h_keys_sorted, d_keys_sorted, npairs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
     cudaMemcpyAsync(h_maxdiag, d_maxdiag, npairs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -169,49 +203,18 @@ int ClassEngine::run_diagonal(double *d_diag, std::string &err) {
 // With the diagonal on the host: per-pair max |(xy|xy)|, sort each sublist (descending), permute the
 // device tables accordingly.
 int ClassEngine::sort_by_diagonal(std::string &err) {
-    int *perm = h_perm;  // pinned; one entry per class pair
-    const double *maxd = reinterpret_cast<const double *>(h_maxdiag);  // natural order, by sublist
-    PermuteTable tab{};
-    int first = 0;
-    // keys: bit patterns of the non-negative maxima order like the doubles themselves; complemented
-    // for a descending sort, index as tie-break (deterministic)
-    struct Key {
-        unsigned long long k;
-        int i;
-        bool operator<(const Key &o) const { return k != o.k ? k < o.k : i < o.i; }
-    };
-    std::vector<Key> keyed;
+    (void)err;
+    // the sort and the permutation already ran on the device (run_diagonal); record the natural maxima
+    // on the host pairs (the shell-quartet path screens against them)
+    const double *maxd = reinterpret_cast<const double *>(h_maxdiag);
     for (size_t si = 0; si < sd->sublists.size(); ++si) {
-        Sublist &s = sd->sublists[si];
+        const Sublist &s = sd->sublists[si];
         const std::vector<int> &nat = nat_ids[si];
-        const int n = (int)nat.size();
         const double *m = maxd + s.meta_off / 2;
-        keyed.resize(n);  // contiguous keys: cache-friendly sort
-        const unsigned long long *mb = h_maxdiag + s.meta_off / 2;
-        for (int i = 0; i < n; ++i) {
-            sd->pairs[nat[i]].maxdiag = m[i];
-            keyed[i] = Key{~mb[i], i};
-        }
-        std::sort(keyed.begin(), keyed.end());
-        for (int i = 0; i < n; ++i) {
-            s.pair_ids[i] = nat[keyed[i].i];
-            perm[s.meta_off / 2 + i] = keyed[i].i;
-        }
-        if (n > 0 && tab.count < kMaxSublists) {
-            tab.d[tab.count++] = PermuteDesc{s.bra_off, s.ket_off, s.meta_off, first, n, s.K, s.nf, s.npad};
-            first += n;
-        }
-    }
-    cudaMemcpyAsync(d_perm, perm, (dev->meta_ints / 2) * sizeof(int), cudaMemcpyHostToDevice, stream);
-    if (first > 0)
-        permute_pairs_kernel<<<first, 64, 0, stream>>>(tab, d_bra_nat, d_meta_nat, d_perm, dev->d_bra, dev->d_ket, dev->d_meta);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        err = std::string("permute pair tables: ") + cudaGetErrorString(e);
-        return -1;
+        for (size_t i = 0; i < nat.size(); ++i) sd->pairs[nat[i]].maxdiag = m[i];
     }
     plan_valid = false;
-    return 1;
+    return 0;
 }
 
 // Number of ket pairs (sorted descending by maxdiag) that pass the shell-level bound against a bra
@@ -234,10 +237,13 @@ static int surviving_prefix(double db, const std::vector<double> &dk, int screen
 int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::string &err) {
     if (plan_valid && plan_screen == screen && plan_thr == thr && plan_rank == rank && plan_world == world) return 0;
     const int ns = (int)sd->sublists.size();
-    std::vector<std::vector<double>> md(ns);
-    for (int s = 0; s < ns; ++s) {
-        md[s].reserve(sd->sublists[s].pair_ids.size());
-        for (int id : sd->sublists[s].pair_ids) md[s].push_back(sd->pairs[id].maxdiag);
+    std::vector<std::vector<double>> md(ns);  // per sublist: maxima in sorted (descending) order
+    {
+        const double *sorted = reinterpret_cast<const double *>(h_keys_sorted);
+        for (int s = 0; s < ns; ++s) {
+            const size_t base = sd->sublists[s].meta_off / 2, n = sd->sublists[s].pair_ids.size();
+            md[s].assign(sorted + base, sorted + base + n);
+        }
     }
     std::vector<long long> table;
     std::vector<ClassJob> jobs;
@@ -449,6 +455,11 @@ ClassEngine::~ClassEngine() {
     if (h_perm) cudaFreeHost(h_perm);
     if (d_maxdiag) cudaFree(d_maxdiag);
     if (h_maxdiag) cudaFreeHost(h_maxdiag);
+    if (d_keys_sorted) cudaFree(d_keys_sorted);
+    if (h_keys_sorted) cudaFreeHost(h_keys_sorted);
+    if (d_iota) cudaFree(d_iota);
+    if (d_seg) cudaFree(d_seg);
+    if (d_sort_temp) cudaFree(d_sort_temp);
     if (h_table) cudaFreeHost(h_table);
     if (h_jobs) cudaFreeHost(h_jobs);
     if (ev_fork) {

@@ -29,6 +29,16 @@ struct ClassPlanLaunch {
     long long total_tiles = 0;
 };
 
+constexpr int kMaxSublists = 48;
+struct PermuteDesc {
+    size_t bra_off, ket_off, meta_off;
+    int first, n, K, nf, npad;
+};
+struct PermuteTable {
+    PermuteDesc d[kMaxSublists];
+    int count;
+};
+
 struct ClassEngine {
     ShellData *sd = nullptr;
     PairTablesDev *dev = nullptr;
@@ -52,6 +62,12 @@ struct ClassEngine {
     size_t h_table_cap = 0;
     ClassJob *h_jobs = nullptr;    // pinned staging
     int *h_perm = nullptr;         // pinned staging
+    unsigned long long *d_keys_sorted = nullptr, *h_keys_sorted = nullptr;  // maxima, sorted per sublist
+    int *d_iota = nullptr, *d_seg = nullptr;
+    void *d_sort_temp = nullptr;
+    size_t sort_temp_bytes = 0;
+    PermuteTable permute_tab{};
+    int permute_blocks = 0;
     double host_ms[4] = {0, 0, 0, 0};  // sort, plan
     ClassJob *d_jobs = nullptr;
     size_t jobs_cap = 0;
