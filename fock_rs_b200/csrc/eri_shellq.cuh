@@ -90,6 +90,11 @@ __device__ __forceinline__ void sq_hermite_dim(double *E, int la, int lb, double
 template <class Sink>
 __global__ void __launch_bounds__(kSqThreads) eri_shellq_kernel(SqLaunch sl, Sink sink) {
     extern __shared__ double s_sq[];
+    // index tables in shared memory: constant memory serialises lane-divergent lookups
+    __shared__ SqTables s_tab;
+    for (int i = threadIdx.x; i < (int)(sizeof(SqTables) / sizeof(int)); i += kSqThreads)
+        reinterpret_cast<int *>(&s_tab)[i] = reinterpret_cast<const int *>(&c_sq)[i];
+    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *acc = s_sq + (size_t)warp * kSqSmemPerWarp;
     double *Rbuf = acc + kSqMaxComp;       // two levels, kSqREntries each
@@ -141,21 +146,21 @@ __global__ void __launch_bounds__(kSqThreads) eri_shellq_kernel(SqLaunch sl, Sin
                             const int deg = L - n;
                             const int cnt = (deg + 1) * (deg + 2) * (deg + 3) / 6;
                             for (int e = lane; e < cnt; e += 32) {
-                                const int t = c_sq.t[e], u = c_sq.u[e], v = c_sq.v[e];
+                                const int t = s_tab.t[e], u = s_tab.u[e], v = s_tab.v[e];
                                 double r;
                                 if (e == 0) {
                                     r = powi_rt(-2.0 * alpha, n) * F[n];
                                 } else if (t == 0 && u == 0) {
-                                    r = Z * prev[c_sq.idx[0][0][v - 1]] + (v > 1 ? (double)(v - 1) * prev[c_sq.idx[0][0][v - 2]] : 0.0);
+                                    r = Z * prev[s_tab.idx[0][0][v - 1]] + (v > 1 ? (double)(v - 1) * prev[s_tab.idx[0][0][v - 2]] : 0.0);
                                 } else if (t == 0) {
-                                    r = Y * prev[c_sq.idx[0][u - 1][v]] + (u > 1 ? (double)(u - 1) * prev[c_sq.idx[0][u - 2][v]] : 0.0);
+                                    r = Y * prev[s_tab.idx[0][u - 1][v]] + (u > 1 ? (double)(u - 1) * prev[s_tab.idx[0][u - 2][v]] : 0.0);
                                 } else {
                                     double second = 0.0;
                                     if (t > 1) {
-                                        second = prev[c_sq.idx[t - 2][u][v]];
+                                        second = prev[s_tab.idx[t - 2][u][v]];
                                         if (fix_r) second *= (double)(t - 1);
                                     }
-                                    r = X * prev[c_sq.idx[t - 1][u][v]] + second;
+                                    r = X * prev[s_tab.idx[t - 1][u][v]] + second;
                                 }
                                 cur[e] = r;
                             }
@@ -185,7 +190,7 @@ __global__ void __launch_bounds__(kSqThreads) eri_shellq_kernel(SqLaunch sl, Sin
                                         for (int t2 = 0; t2 <= cx + dx; ++t2)
                                             for (int u2 = 0; u2 <= cy + dy; ++u2)
                                                 for (int v2 = 0; v2 <= cz + dz; ++v2) {
-                                                    const double term = eb * ekx[t2] * eky[u2] * ekz[v2] * R[c_sq.idx[t1 + t2][u1 + u2][v1 + v2]];
+                                                    const double term = eb * ekx[t2] * eky[u2] * ekz[v2] * R[s_tab.idx[t1 + t2][u1 + u2][v1 + v2]];
                                                     s += ((t2 + u2 + v2) & 1) ? -term : term;
                                                 }
                                     }
