@@ -54,26 +54,61 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (spawning
+    nvidia-smi every 100 ms perturbs a 3 ms step measurably); nvidia-smi is the fallback."""
 
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index = index
-        self.samples = []
+        self.samples = []  # (sm_mhz, reason bitmask)
         self._stop = threading.Event()
         self._t = None
+        self._nv = None
+        self._h = None
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self._h, pynvml.NVML_CLOCK_SM)  # first call is slow
+        except Exception:
+            self._h = None
+
+    def _sample_nvml(self):
+        nv = self._nv
+        mhz = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        self.samples.append((float(mhz), int(reasons)))
+
+    def _sample_smi(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        f = [x.strip() for x in out.split(",")]
+        bits = 0
+        for i, b in enumerate((0x8, 0x40, 0x20, 0x4)):
+            if len(f) > 2 + i and f[2 + i].lower().startswith("active"):
+                bits |= b
+        self.max_mhz = float(f[1])
+        self.samples.append((float(f[0]), bits))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                if self._h is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.003 if self._h is not None else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -86,12 +121,13 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(self.samples)}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        sm = sorted(s[0] for s in self.samples)
+        bits = 0
+        for _, r in self.samples:
+            bits |= r
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": [n for b, n in self.NAMES.items() if bits & b],
+                "samples": len(self.samples), "source": "nvml" if self._h is not None else "nvidia-smi"}
 
 
 # --------------------------------------------------------------------------------------------
@@ -258,7 +294,11 @@ def run_ours(args):
     storage = _lib.STORAGE_INCORE if args.storage == "incore" else _lib.STORAGE_DIRECT
     b = FockBuilder(flat, mode=mode, screen=screen, storage=storage, device=local, rank=rank, world=world, keep_eri=False,
                     incore_shard=1 if args.incore_shard == "build" else 0)
-    stream = torch.cuda.current_stream()
+    # one explicit (non-default) stream for the library's launches, the NCCL calls and the timing events:
+    # torch.cuda.Event only sees the stream it is recorded on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     b.set_stream(stream.cuda_stream)
     rng = np.random.default_rng(20261017)
     Dh = rng.uniform(-1.0, 1.0, (n, n))
@@ -310,13 +350,13 @@ def run_ours(args):
         barrier()
         t_dev_ms = timed(step_device, args.steps)
         barrier()
-    tm = b.timings()
-    st = b.stats()
-    for _ in range(2):
-        step_host()
-    barrier()
-    t_host_ms = timed(step_host, args.steps)
-    barrier()
+        tm = b.timings()
+        st = b.stats()
+        for _ in range(2):
+            step_host()
+        barrier()
+        t_host_ms = timed(step_host, args.steps)
+        barrier()
     g_host = step_host()
     # max over ranks
     if dist is not None:
@@ -347,7 +387,9 @@ def run_ours(args):
         roof_eri = {"bound": "fp64", "achieved": eri_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": eri_tf / fp64_peak if fp64_peak else None,
                     "traffic": None, "kernel": "eri_class_kernel<*> (the 8 class launches of one build, CUDA events around them)",
                     "note": "model flops of the quartets evaluated (SURVEY.md 8d formula) / time between the events bracketing the class launches; peak = DFMA-chain probe measured in this run"}
-        roof_g = {"bound": "hbm", "achieved": g_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": g_gbs / hbm_peak, "traffic": None,
+        # DRAM bytes of one symv launch from the committed ncu --set full capture (profiles/r01_*_ncu_full_w16_refcut.md)
+        symv_traffic = 1.894e9 if (args.workload == "w16" and world == 1 and storage == _lib.STORAGE_INCORE) else None
+        roof_g = {"bound": "hbm", "achieved": g_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": g_gbs / hbm_peak, "traffic": symv_traffic,
                   "kernel": "symv_packed_kernel (+ pack/unpack)", "note": f"8 B per stored supermatrix element per rank / device time of one G build; peak = {peak_src}"}
         line = {
             "metric": METRIC, "value": nq / (ms_step * 1e-3), "unit": "shell_quartets/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -386,7 +428,8 @@ def quick_config(workload, storage, screen, rank, world, local, steps=3):
     st_mode = _lib.STORAGE_INCORE if storage == "incore" else _lib.STORAGE_DIRECT
     b = FockBuilder(flat, screen=_lib.SCREEN_REFERENCE if screen == "ref" else _lib.SCREEN_OFF, storage=st_mode, device=local, rank=rank,
                     world=world, keep_eri=False)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.current_stream()  # run_ours installed an explicit stream as the current one
+    assert stream.cuda_stream != 0
     b.set_stream(stream.cuda_stream)
     rng = np.random.default_rng(20261017)
     Dh = rng.uniform(-1.0, 1.0, (n, n))
@@ -429,7 +472,7 @@ def quick_config(workload, storage, screen, rank, world, local, steps=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="w16", choices=sorted(WORKLOADS))
