@@ -403,6 +403,7 @@ int fock_eri_build(fock_ctx *ctx) {
             std::string err;
             FOCK_TRY(make_plan_timed(ctx, thr, b_rank, b_world));
             TensorSink sink{Vp, Pp, ctx->d_diag, thr, ctx->opts.screen};
+            if (getenv("FOCK_SINK_MASK")) sink.mask = (size_t)strtoull(getenv("FOCK_SINK_MASK"), nullptr, 0);  // wrong results, timing only
             FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_k0, st));
             const int l = cs->engine.run_plan(sink, err);
             FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_k1, st));

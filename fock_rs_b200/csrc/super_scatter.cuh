@@ -70,8 +70,8 @@ __device__ __forceinline__ void for_each_super_target(int i, int j, int k, int l
 
 // P[slot] += contribution (in-core supermatrix formation fused into the integral kernels); P uses the
 // row-padded layout ptri() of device_math.cuh
-__device__ __forceinline__ void scatter_super(double *P, int i, int j, int k, int l, double v) {
-    for_each_super_target(i, j, k, l, v, [&](size_t ab, size_t cd, double c) { atomicAdd(P + ptri(ab, cd), c); });
+__device__ __forceinline__ void scatter_super(double *P, int i, int j, int k, int l, double v, size_t mask = ~(size_t)0) {
+    for_each_super_target(i, j, k, l, v, [&](size_t ab, size_t cd, double c) { atomicAdd(P + (ptri(ab, cd) & mask), c); });
 }
 
 // y += P_contribution * d (integral-direct digestion): the same elements applied on the fly.
