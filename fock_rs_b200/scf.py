@@ -171,3 +171,100 @@ def try_scf(atoms: Sequence[Atom], max_iters: int, epsilon: float, molecule_char
             return None
         log.debug("Iteration %d: max error (loss): %.5e, energy: %.5f", it, error, e_el + e_nuc)
     return None
+
+
+def try_scf_device(atoms: Sequence[Atom], max_iters: int, epsilon: float, molecule_charge: int = 0, mode=0, screen=0, storage=0,
+                   device: int = 0) -> Optional[HartreeFockResult]:
+    """Device-resident variant of `try_scf`: the density, Fock and DIIS matrices stay
+    in HBM, FDS - SDF / the similarity transforms run through cuBLAS and the two eigensolves through
+    cuSOLVER (torch.linalg), and G comes from `fock_build_g_device` -- no N x N matrix crosses PCIe inside
+    the loop; one scalar (the DIIS error) is read back per iteration for the convergence test.
+    Same algorithm and constants as `try_scf` (scf/src/lib.rs:73-258)."""
+    import torch
+
+    from .fock import FockBuilder
+
+    atoms = list(atoms)
+    flat = flatten(molecule_basis(atoms))
+    n = flat.n_basis
+    n_electrons = sum(a.electron_count() for a in atoms) - molecule_charge
+    n_occ = n_electrons // 2
+    e_nuc = nuclear_repulsion(atoms)
+    dev = torch.device("cuda", device)
+    builder = FockBuilder(flat, mode=mode, screen=screen, storage=storage, device=device, keep_eri=False)
+    try:
+        stream = torch.cuda.current_stream(dev)
+        own_stream = stream.cuda_stream == 0  # legacy default stream: the library keeps its own and we fence around it
+        if not own_stream:
+            builder.set_stream(stream.cuda_stream)
+        nuc_pos = np.array([a.position for a in atoms], dtype=np.float64)
+        nuc_chg = np.array([float(a.atom_type) for a in atoms], dtype=np.float64)
+        S_h, T_h, V_h = builder.one_electron(nuc_pos, nuc_chg)
+        builder.eri_build()
+        S = torch.from_numpy(np.ascontiguousarray(S_h)).to(dev)
+        H = torch.from_numpy(np.ascontiguousarray(T_h + V_h)).to(dev)
+
+        def mirror_upper(m):
+            u = torch.triu(m)
+            return u + torch.triu(m, 1).T
+
+        _, u = torch.linalg.eigh(S)
+        diag = u.T @ (S @ u)
+        X = u @ (torch.diag(1.0 / torch.sqrt(torch.diagonal(diag))) @ u.T)
+
+        def density_from(coeffs):
+            c = coeffs[:, :n_occ]
+            return mirror_upper(2.0 * (c @ c.T))
+
+        hd = torch.diagonal(H)
+        h_eht = mirror_upper(0.875 * S * (hd[:, None] + hd[None, :]))
+        _, cp = torch.linalg.eigh(X.T @ (h_eht @ X))
+        D = density_from(X @ cp).contiguous()
+        G = torch.empty_like(D)
+        prev_f, prev_e = deque(), deque()
+        energies, errors = [], []
+        for it in range(max_iters + 1):
+            if own_stream:
+                torch.cuda.synchronize(dev)
+            builder.build_g_device(D.data_ptr(), G.data_ptr())  # symmetric: row- and column-major images coincide
+            if own_stream:
+                torch.cuda.synchronize(dev)
+            guess = G.clone()
+            fock = H + guess
+            err_m = fock @ D @ S - S @ D @ fock
+            error = float(torch.max(torch.abs(err_m)))  # the one scalar read back per iteration
+            prev_e.append(err_m)
+            prev_f.append(fock)
+            if len(prev_e) > 16:
+                prev_e.popleft()
+                prev_f.popleft()
+            fock_x = fock
+            if len(prev_f) >= 5:
+                m = len(prev_e)
+                E = torch.stack([e.reshape(-1) for e in prev_e])
+                B = torch.zeros((m + 1, m + 1), dtype=torch.float64, device=dev)
+                B[:m, :m] = E @ E.T
+                B[m, :m] = -1.0
+                B[:m, m] = -1.0
+                rhs = torch.zeros(m + 1, dtype=torch.float64, device=dev)
+                rhs[m] = -1.0
+                try:
+                    c = torch.linalg.inv(B) @ rhs
+                    if bool(torch.all(torch.isfinite(c))):
+                        fock_x = sum(c[i] * prev_f[i] for i in range(m))
+                except Exception:
+                    pass
+            orb_e, cp = torch.linalg.eigh(X.T @ (fock_x @ X))
+            coeffs = X @ cp
+            D = density_from(coeffs).contiguous()
+            e_el = 0.5 * float(torch.trace(D @ (2.0 * H + guess)))
+            energies.append(e_el + e_nuc)
+            errors.append(error)
+            if error < epsilon or it == max_iters:
+                return HartreeFockResult(orb_e.cpu().numpy(), D.cpu().numpy(), coeffs.cpu().numpy(), e_el, e_nuc + e_el, it, n_electrons, n,
+                                         energies, errors)
+            elif not (math.isfinite(error) and error >= 2.2250738585072014e-308):
+                return None
+        return None
+    finally:
+        builder.close()

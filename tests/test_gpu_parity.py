@@ -309,3 +309,18 @@ def test_scf_with_d_shells_water_631gss():
     ro = try_scf(atoms, 100, 1e-6, 0, engine=OracleEngine(oracle.FAITHFUL, fast=True))
     assert r is not None and ro is not None and r.iterations == ro.iterations
     assert abs(r.total_energy - ro.total_energy) <= E_TOL
+
+
+def test_device_resident_scf_matches_host_loop():
+    """the SCF step with D/F/DIIS resident on the GPU (cuBLAS/cuSOLVER through torch)
+    gives the same energies and iteration counts as the host loop."""
+    import torch
+
+    from fock_rs_b200.scf import try_scf_device
+
+    for mol, basis, energy, iters in [("water", "STO-3G", -74.9874357034, 7), ("water", "6-31G", -76.0126589918, 12)]:
+        atoms = atoms_for(mol, basis)
+        with torch.cuda.stream(torch.cuda.Stream()):
+            r = try_scf_device(atoms, 100, 1e-6, 0)
+        assert r is not None and r.iterations == iters
+        assert abs(r.total_energy - energy) <= 2e-8
