@@ -136,19 +136,21 @@ class ClockSampler:
 
 
 def count_surviving(diag, thr=1e-6):
-    """Number of unordered pairs {xy, zw}, xy != zw, with sqrt(d_xy * d_zw) > thr (the reference's cut)."""
-    d = np.sort(np.asarray(diag))[::-1]
-    n = d.size
+    """Number of unordered pairs {xy, zw}, xy != zw, with sqrt(d_xy * d_zw) > thr (the reference's cut),
+    counted in O(P log P): with the diagonal sorted descending, the partners of entry i are a prefix."""
+    d = np.sort(np.asarray(diag, dtype=np.float64))[::-1]
+    d = np.where(np.isfinite(d) & (d > 0), d, 0.0)
+    asc = d[::-1]
     total = 0
-    step = 2048
-    for i0 in range(0, n, step):
-        blk = d[i0 : i0 + step]
-        est = np.sqrt(np.outer(blk, d))
-        ok = est > thr
-        # count j > i only
-        idx = np.arange(i0, min(i0 + step, n))[:, None]
-        total += int(np.count_nonzero(ok & (np.arange(n)[None, :] > idx)))
-    return total
+    with np.errstate(divide="ignore"):
+        need = np.where(d > 0, (thr * thr) / d, np.inf)  # d_j must exceed this
+    # number of entries strictly greater than need[i] = n - searchsorted(asc, need[i], side='right')
+    cnt = d.size - np.searchsorted(asc, need, side="right")
+    idx = np.arange(d.size)
+    # partners j != i: entry i itself is inside its own prefix iff d_i * d_i > thr^2
+    self_in = cnt > idx
+    total = int(np.sum(cnt) - np.count_nonzero(self_in))
+    return total // 2
 
 
 def cpu_baseline(workload, screen_ref, budget_s, quartets_unique):
@@ -264,7 +266,8 @@ def config_dict(args, flat):
         "storage": args.storage,
         "mode": args.mode,
         "screening": "reference 1e-6 cut (basis/src/electron_tensor.rs:134-155)" if args.screen == "ref" else "off",
-        "l2": "inputs larger than L2 (packed tensor) " if flat.n_basis >= 150 else "L2 flushed between timed steps (256 MiB write)",
+        "l2": ("inputs larger than L2 (packed supermatrix streamed every step)" if (flat.n_basis >= 150 and args.storage == "incore")
+               else "L2 flushed between timed steps (256 MiB write, outside the timed region)"),
         "parallelism": (f"shell-quartet tiles sharded over {args.gpus} rank(s); one all-reduce of G per step"
                         + ("" if args.gpus == 1 or args.storage != "incore" else f"; in-core sharding = {args.incore_shard}")),
     }
@@ -305,7 +308,8 @@ def run_ours(args):
     Dh = np.asfortranarray(0.5 * (Dh + Dh.T))
     D = torch.from_numpy(np.ascontiguousarray(Dh.T)).cuda()  # column-major image
     G = torch.empty_like(D)
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda") if n < 150 else None
+    needs_flush = n < 150 or storage == _lib.STORAGE_DIRECT  # working set (pair tables, D, y) fits the 126 MB L2
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda") if needs_flush else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -375,15 +379,20 @@ def run_ours(args):
     others = []
     if not args.no_other_configs:
         # all ranks take part (sharded runs); rank 0 reports
-        others.append(quick_config("benzene", "incore", "ref", rank, world, local))
-        others.append(quick_config("alkane40", "direct", "ref", rank, world, local))
+        for wl, stor in (("benzene", "incore"), ("w16", "incore"), ("alkane40", "direct")):
+            if (wl, stor) != (args.workload, args.storage):
+                others.append(quick_config(wl, stor, "ref", rank, world, local, incore_shard=1 if args.incore_shard == "build" else 0))
     if rank == 0:
         eri_tf = st["model_flops"] / (tm["class_kernels_ms"] * 1e-3) * 1e-12 if tm["class_kernels_ms"] > 0 else 0.0
-        g_gbs = 8.0 * nelem / world / max(tm["g_device_ms"], 1e-9) * 1e-6
-        parts = {"diag_ms": tm["diag_ms"], "eri_ms": tm["eri_ms"], "supermatrix_ms": tm["supermatrix_ms"], "g_ms": tm["g_device_ms"],
+        streamed = nelem / (world if (world > 1 and args.incore_shard == "digest") else 1)
+        g_gbs = 8.0 * streamed / max(tm["g_device_ms"], 1e-9) * 1e-6 if storage == _lib.STORAGE_INCORE else 0.0
+        parts = {"diag_ms": tm["diag_ms"] if not direct else 0.0, "eri_ms": tm["eri_ms"] if not direct else 0.0,
+                 "supermatrix_ms": tm["supermatrix_ms"], "g_ms": tm["g_device_ms"],
                  "host_sort_ms_inside_eri": tm["host_sort_ms"], "host_plan_ms_inside_eri": tm["host_plan_ms"],
                  "class_kernels_ms_inside_eri": tm["class_kernels_ms"]}
         dominant = max(("diag_ms", "eri_ms", "supermatrix_ms", "g_ms"), key=parts.get)
+        if direct:
+            dominant = "class_kernels (inside the fused G build)"
         roof_eri = {"bound": "fp64", "achieved": eri_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": eri_tf / fp64_peak if fp64_peak else None,
                     "traffic": None, "kernel": "eri_class_kernel<*> (the 8 class launches of one build, CUDA events around them)",
                     "note": "model flops of the quartets evaluated (SURVEY.md 8d formula) / time between the events bracketing the class launches; peak = DFMA-chain probe measured in this run"}
@@ -398,8 +407,8 @@ def run_ours(args):
             "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "shell_quartets/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 8 * n * n, "d2h_bytes_per_step": 8 * n * n},
             "gpu_launches": int((st["launches_build"] + st["launches_g"]) * args.steps),
             "clocks": clocks.summary(),
-            "roofline": roof_g if dominant == "g_ms" else roof_eri,
-            "roofline_eri": roof_eri, "roofline_digest": roof_g,
+            "roofline": roof_g if (dominant == "g_ms" and storage == _lib.STORAGE_INCORE) else roof_eri,
+            "roofline_eri": roof_eri, "roofline_digest": roof_g if storage == _lib.STORAGE_INCORE else None,
             "breakdown_ms": parts, "dominant": dominant,
             "stats": {"shells": nshell, "shell_quartets_unique": nq, "class_shell_quartets_evaluated": st["shell_quartets_evaluated"],
                       "prim_quartets_evaluated": st["prim_quartets_evaluated"], "model_flops": st["model_flops"], "warp_tiles": st["warp_tiles"], "device_vs_host_path_max_abs_diff": agree},
@@ -415,7 +424,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def quick_config(workload, storage, screen, rank, world, local, steps=3):
+def quick_config(workload, storage, screen, rank, world, local, steps=5, incore_shard=1):
     """Secondary configs reported beside the headline workload (same step definition, device-resident D/G)."""
     import torch
 
@@ -427,7 +436,7 @@ def quick_config(workload, storage, screen, rank, world, local, steps=3):
     nq, _ = unique_shell_quartets(flat)
     st_mode = _lib.STORAGE_INCORE if storage == "incore" else _lib.STORAGE_DIRECT
     b = FockBuilder(flat, screen=_lib.SCREEN_REFERENCE if screen == "ref" else _lib.SCREEN_OFF, storage=st_mode, device=local, rank=rank,
-                    world=world, keep_eri=False)
+                    world=world, keep_eri=False, incore_shard=incore_shard)
     stream = torch.cuda.current_stream()  # run_ours installed an explicit stream as the current one
     assert stream.cuda_stream != 0
     b.set_stream(stream.cuda_stream)
@@ -462,10 +471,12 @@ def quick_config(workload, storage, screen, rank, world, local, steps=3):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0])
     tm, stt = b.timings(), b.stats()
+    b_len = b._L.fock_packed_len(n)
     b.close()
     return {"workload": WORKLOADS[workload][0], "n_basis": n, "storage": storage, "screening": screen, "ms_per_step": ms,
             "shell_quartets_per_s": nq / (ms * 1e-3), "shell_quartets_unique": nq, "shell_quartets_evaluated": stt["shell_quartets_evaluated"],
             "class_kernels_ms": tm["class_kernels_ms"], "g_device_ms": tm["g_device_ms"],
+            "digest_hbm_gbs": (8.0 * b_len / (world if incore_shard == 0 else 1) / (tm["g_device_ms"] * 1e-3) * 1e-9) if storage == "incore" else None,
             "class_kernels_model_tflops": stt["model_flops"] / (tm["class_kernels_ms"] * 1e-3) * 1e-12 if tm["class_kernels_ms"] > 0 else None}
 
 
@@ -475,8 +486,8 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="w16", choices=sorted(WORKLOADS))
-    ap.add_argument("--storage", default="incore", choices=["incore", "direct"])
+    ap.add_argument("--workload", default="alkane40", choices=sorted(WORKLOADS))
+    ap.add_argument("--storage", default=None, choices=["incore", "direct"], help="default: direct for alkane40/w32, in-core otherwise")
     ap.add_argument("--screen", default="ref", choices=["ref", "off"])
     ap.add_argument("--mode", default="faithful", choices=["faithful", "accurate"])
     ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU work for the cpu_baseline sample")
@@ -486,6 +497,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the secondary workloads reported in other_configs")
     args = ap.parse_args()
+    if args.storage is None:
+        args.storage = "direct" if args.workload in ("alkane40", "w32") else "incore"
     if args.impl == "reference":
         run_reference(args)
     else:
