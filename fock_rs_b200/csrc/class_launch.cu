@@ -445,6 +445,7 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
 
 template int ClassEngine::run_plan<TensorSink>(const TensorSink &, std::string &);
 template int ClassEngine::run_plan<DirectSink>(const DirectSink &, std::string &);
+template int ClassEngine::run_plan<BlockDirectSink>(const BlockDirectSink &, std::string &);
 
 ClassEngine::~ClassEngine() {
     if (d_table) cudaFree(d_table);

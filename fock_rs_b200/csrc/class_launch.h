@@ -12,6 +12,7 @@ namespace fock {
 
 struct TensorSink;
 struct DirectSink;
+struct BlockDirectSink;
 struct ClassJob;
 
 struct ClassStats {

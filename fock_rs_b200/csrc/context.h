@@ -35,6 +35,7 @@ struct fock_ctx {
     double *d_P = nullptr;     // [nelem] supermatrix (ij|kl) - 1/4 (ik|jl) - 1/4 (il|jk)
     double *d_dvec = nullptr;  // [npair] packed density
     double *d_yvec = nullptr;  // [npair] packed result
+    double *d_Ds = nullptr, *d_A = nullptr;  // [N*N] symmetrised density / block-digest accumulator (direct mode)
     double *d_D = nullptr, *d_G = nullptr;  // [N*N] staging for the host-buffer entry point
     double *h_pinned = nullptr;              // [2*N*N] pinned staging
 

@@ -72,6 +72,8 @@ int ensure_g_buffers(fock_ctx *ctx) {
     const size_t nn = (size_t)ctx->N * ctx->N;
     if (!ctx->d_dvec) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_dvec, ctx->npair * sizeof(double)));
     if (!ctx->d_yvec) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_yvec, ctx->npair * sizeof(double)));
+    if (!ctx->d_Ds) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_Ds, nn * sizeof(double)));
+    if (!ctx->d_A) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_A, nn * sizeof(double)));
     if (!ctx->d_D) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_D, nn * sizeof(double)));
     if (!ctx->d_G) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_G, nn * sizeof(double)));
     if (!ctx->h_pinned) FOCK_CUDA_TRY(ctx, cudaMallocHost((void **)&ctx->h_pinned, 2 * nn * sizeof(double)));
@@ -270,7 +272,7 @@ void fock_destroy(fock_ctx *c) {
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     void *ptrs[] = {ctx->d_center, ctx->d_angular, ctx->d_primoff, ctx->d_exp,  ctx->d_coef, ctx->d_boys_lut,
                     ctx->d_boys_tab, ctx->d_diag,   ctx->d_V,       ctx->d_P,    ctx->d_dvec, ctx->d_yvec,
-                    ctx->d_D,      ctx->d_G,       ctx->pairs.d_bra, ctx->pairs.d_ket, ctx->pairs.d_meta,
+                    ctx->d_D,      ctx->d_G,       ctx->d_Ds,      ctx->d_A,    ctx->pairs.d_bra, ctx->pairs.d_ket, ctx->pairs.d_meta,
                     ctx->pairs.d_shell_bf, ctx->pairs.d_maxdiag, ctx->cs.d_bf_class_ok, ctx->cs.d_bf_covered, ctx->cs.d_counter, ctx->cs.d_boys_poly};
     ctx->cs.sq.destroy();
     for (void *p : ptrs)
@@ -603,15 +605,30 @@ int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev) {
         ClassState *cs = cls(ctx);
         const double thr = screen_threshold(ctx->opts);
         pack_density_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(D_dev, ctx->N, ctx->d_dvec, ctx->d_yvec, ctx->npair);
-        diag_digest_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(ctx->d_diag, ctx->npair, ctx->opts.rank, ctx->opts.world,
-                                                                               ctx->d_dvec, ctx->d_yvec);
-        launches += 2;
+        // the class kernels digest shell blocks into the full matrix A (BlockDirectSink); the general paths
+        // below still digest integral by integral into the packed y; combine_g_kernel adds the two
+        static const bool legacy_sink = getenv("FOCK_LEGACY_DIRECT_SINK") != nullptr;
+        const unsigned nn_blocks = (unsigned)(((size_t)ctx->N * ctx->N + 255) / 256);
+        symm_density_kernel<<<nn_blocks, 256, 0, st>>>(D_dev, ctx->N, ctx->d_Ds, ctx->d_A);
+        if (legacy_sink)
+            diag_digest_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(ctx->d_diag, ctx->npair, ctx->opts.rank,
+                                                                                   ctx->opts.world, ctx->d_dvec, ctx->d_yvec);
+        else
+            diag_digest_block_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(
+                ctx->d_diag, ctx->npair, ctx->opts.rank, ctx->opts.world, ctx->d_Ds, ctx->N, ctx->d_A);
+        launches += 3;
         if (!ctx->shells.pairs.empty()) {
             std::string err;
             FOCK_TRY(make_plan_timed(ctx, thr, ctx->opts.rank, ctx->opts.world));
-            DirectSink sink{ctx->d_yvec, ctx->d_dvec, ctx->d_diag, thr, ctx->opts.screen};
             FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_k0, st));
-            const int l = cs->engine.run_plan(sink, err);
+            int l;
+            if (legacy_sink) {
+                DirectSink sink{ctx->d_yvec, ctx->d_dvec, ctx->d_diag, thr, ctx->opts.screen};
+                l = cs->engine.run_plan(sink, err);
+            } else {
+                BlockDirectSink sink{ctx->d_A, ctx->d_Ds, ctx->d_diag, thr, ctx->opts.screen, ctx->N};
+                l = cs->engine.run_plan(sink, err);
+            }
             FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_k1, st));
             if (l < 0) {
                 ctx->err = err;
@@ -638,7 +655,7 @@ int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev) {
                 ctx->opts.rank, ctx->opts.world, ctx->d_dvec, ctx->d_yvec);
             launches += 1;
         }
-        unpack_result_kernel<<<(unsigned)(((size_t)ctx->N * ctx->N + 255) / 256), 256, 0, st>>>(ctx->d_yvec, ctx->N, G_dev);
+        combine_g_kernel<<<nn_blocks, 256, 0, st>>>(ctx->d_yvec, ctx->d_A, ctx->N, G_dev);
         launches += 1;
     }
     FOCK_CUDA_TRY(ctx, cudaGetLastError());

@@ -85,6 +85,41 @@ __global__ void diag_digest_kernel(const double *__restrict__ diag, size_t npair
     digest_super(y, d, (int)x, (int)yy, (int)x, (int)yy, diag[xy]);
 }
 
+// ---- shell-block direct digestion (BlockDirectSink, eri_class.cuh): its O(N^2) companions.
+// Ds = (D + D^T)/2 (D column-major N x N), A = 0.
+__global__ void symm_density_kernel(const double *__restrict__ D, int n, double *__restrict__ Ds, double *__restrict__ A) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const size_t i = idx % n, j = idx / n;
+    Ds[idx] = 0.5 * (D[i + j * (size_t)n] + D[j + i * (size_t)n]);
+    A[idx] = 0.0;
+}
+
+// the diagonal integrals (xy|xy) in the same weighted form: w = v (x==y ? 1/4 : 1) / 2
+__global__ void diag_digest_block_kernel(const double *__restrict__ diag, size_t npair, int rank, int world,
+                                         const double *__restrict__ Ds, int n, double *__restrict__ A) {
+    const size_t xy = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (xy >= npair || (int)(xy % (size_t)world) != rank) return;
+    size_t x, y;
+    untri(xy, x, y);
+    const double w = diag[xy] * (x == y ? 0.125 : 0.5);
+    if (w == 0.0) return;
+    const size_t N = (size_t)n;
+    const double Dxy = Ds[x * N + y];
+    atomicAdd(A + x * N + y, 4.0 * w * Dxy - 0.5 * w * Dxy);  // both Coulomb terms and the (xy|yx) exchange term
+    atomicAdd(A + y * N + x, -0.5 * w * Dxy);
+    atomicAdd(A + x * N + x, -0.5 * w * Ds[y * N + y]);
+    atomicAdd(A + y * N + y, -0.5 * w * Ds[x * N + x]);
+}
+
+// G (column-major N x N) = packed y (general-path contributions) + A + A^T
+__global__ void combine_g_kernel(const double *__restrict__ y, const double *__restrict__ A, int n, double *__restrict__ G) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)n * n) return;
+    const size_t i = idx % n, j = idx / n;
+    G[idx] = y[i >= j ? tri(i, j) : tri(j, i)] + (A[i * (size_t)n + j] + A[j * (size_t)n + i]);  // exactly symmetric
+}
+
 // ---- batch of arbitrary function quartets (fock_eri_batch)
 __global__ void generic_batch_kernel(BasisDev bs, BoysTables bt, int mode, const int *quartets, size_t n, double *out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
