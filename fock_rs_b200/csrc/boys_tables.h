@@ -15,7 +15,7 @@ namespace fock {
 constexpr int kBoysPolyIntervals = 200;  // T in [0, 30), width 0.15 (the reference's DT)
 constexpr int kBoysPolyDegree = 7;
 constexpr int kBoysPolyCoefs = kBoysPolyDegree + 1;
-constexpr int kBoysPolyOrders = 5;  // F_0 .. F_4 (s and p shell classes)
+constexpr int kBoysPolyOrders = 9;  // F_0 .. F_8 (shell classes up to (dd|dd))
 // accurate mode: exact F_n on [0, 40.05) with the same interval width
 constexpr int kBoysAccIntervals = 267;
 

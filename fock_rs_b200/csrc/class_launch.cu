@@ -10,24 +10,29 @@
 #include "../../include/fock_b200.h"
 #include "class_launch.h"
 #include "eri_class.cuh"
+#include "eri_shellq.cuh"
 
 namespace fock {
 
 namespace {
 
-const int kClsLA[3] = {0, 1, 1}, kClsLB[3] = {0, 0, 1};
-
 template <int LA, int LB, int LC, int LD, int KC0, int KCN, class Sink>
 void launch_mode(const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, cudaStream_t st) {
     const size_t smem = boys_smem_doubles(LA + LB + LC + LD, cl.boys_ni) * sizeof(double);
+    constexpr int NAB = ncart_c(LA) * ncart_c(LB);
     if (mode & FOCK_MODE_FIX_R_BIT)
-        eri_class_kernel<LA, LB, LC, LD, true, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
+        eri_class_kernel<LA, LB, LC, LD, 1, 0, NAB, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
     else
-        eri_class_kernel<LA, LB, LC, LD, false, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
+        eri_class_kernel<LA, LB, LC, LD, 0, 0, NAB, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
 }
 
+// pair classes: 0 ss, 1 ps, 2 pp (here); 3 ds, 4 dp, 5 dd bras in dclass_*.cu; returns 0 when no
+// register-resident kernel exists for the class pair
 template <class Sink>
 int launch_class(int cb, int ck, const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, cudaStream_t st) {
+    if (cb == 3) return launch_dclass_ds(ck, cl, sink, grid, st);
+    if (cb == 4) return launch_dclass_dp(ck, cl, sink, grid, st);
+    if (cb == 5) return launch_dclass_dd(ck, cl, sink, grid, st);
     switch (cb * 3 + ck) {
         case 0: launch_mode<0, 0, 0, 0, 0, 1>(cl, sink, mode, grid, st); return 1;
         case 3: launch_mode<1, 0, 0, 0, 0, 1>(cl, sink, mode, grid, st); return 1;
@@ -47,9 +52,9 @@ template <int LA, int LB, int KC0, int KCN>
 void launch_diag_mode(const DiagLaunch &dl, const DiagSink &sink, int mode, dim3 grid, cudaStream_t st) {
     const size_t smem = boys_smem_doubles(2 * (LA + LB), dl.boys_ni) * sizeof(double);
     if (mode & FOCK_MODE_FIX_R_BIT)
-        eri_diag_kernel<LA, LB, true, KC0, KCN><<<grid, kClassThreads, smem, st>>>(dl, sink);
+        eri_diag_kernel<LA, LB, 1, KC0, KCN><<<grid, kClassThreads, smem, st>>>(dl, sink);
     else
-        eri_diag_kernel<LA, LB, false, KC0, KCN><<<grid, kClassThreads, smem, st>>>(dl, sink);
+        eri_diag_kernel<LA, LB, 0, KC0, KCN><<<grid, kClassThreads, smem, st>>>(dl, sink);
 }
 
 // sorted tables from the natural-order master: position i of a sublist takes natural pair perm[i].
@@ -73,6 +78,24 @@ __global__ void permute_pairs_kernel(PermuteTable tab, const double *__restrict_
         ok[(size_t)e * d.npad] = v;  // e = ij*nf + f
     }
     if (threadIdx.x < 2) meta[d.meta_off + 2 * i + threadIdx.x] = meta_nat[d.meta_off + 2 * src + threadIdx.x];
+}
+
+// per-pair max |(xy|xy)| of the pairs [first, first+n) of the natural-order meta table, from the
+// basis-function diagonal (sublists with a d shell: their diagonal comes from the generic kernel)
+__global__ void class_pairmax_kernel(const int *__restrict__ meta_nat, const int *__restrict__ shell_bf, int first, int n,
+                                     const double *__restrict__ diag, unsigned long long *__restrict__ maxdiag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int shA = meta_nat[2 * (first + i)], shB = meta_nat[2 * (first + i) + 1];
+    double m = 0.0;
+    for (int ca = 0; ca < 6; ++ca)
+        for (int cb = 0; cb < 6; ++cb) {
+            const int x = shell_bf[shA * 6 + ca], y = shell_bf[shB * 6 + cb];
+            if (x < 0 || y < 0) continue;
+            const double d = fabs(diag[x >= y ? tri(x, y) : tri(y, x)]);
+            if (!(d <= m)) m = (d == d) ? d : __longlong_as_double(0x7ff0000000000000LL);
+        }
+    maxdiag[first + i] = (unsigned long long)__double_as_longlong(m);
 }
 
 }  // namespace
@@ -105,10 +128,15 @@ int ClassEngine::upload_master(std::string &err) {
     std::vector<int> sbf(sd->shells.size() * 6);
     for (size_t s = 0; s < sd->shells.size(); ++s)
         for (int c = 0; c < 6; ++c) sbf[s * 6 + c] = sd->shells[s].bf[c];
-    if ((e = cudaMalloc((void **)&dev->d_shell_bf, sbf.size() * 4 + 8)) != cudaSuccess) {
+    std::vector<double> sscale(sd->shells.size() * 6);
+    for (size_t s = 0; s < sd->shells.size(); ++s)
+        for (int c = 0; c < 6; ++c) sscale[s * 6 + c] = sd->shells[s].scale[c];
+    if ((e = cudaMalloc((void **)&dev->d_shell_bf, sbf.size() * 4 + 8)) != cudaSuccess ||
+        (e = cudaMalloc((void **)&d_shell_scale, sscale.size() * 8 + 8)) != cudaSuccess) {
         err = std::string("shell table: ") + cudaGetErrorString(e);
         return 1;
     }
+    cudaMemcpy(d_shell_scale, sscale.data(), sscale.size() * 8, cudaMemcpyHostToDevice);
     cudaMemcpyAsync(d_bra_nat, bra.data(), bra.size() * 8, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(dev->d_bra, bra.data(), bra.size() * 8, cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(dev->d_ket, ket.data(), ket.size() * 8, cudaMemcpyHostToDevice, stream);
@@ -173,12 +201,30 @@ int ClassEngine::run_diagonal(double *d_diag, std::string &err) {
         } else if (s.cls == 1) {
             launch_diag_mode<1, 0, 0, 3>(dl, sink, mode, grid, stream);
             launches += 1;
-        } else {
+        } else if (s.cls == 2) {
             launch_diag_mode<1, 1, 0, 3>(dl, sink, mode, grid, stream);
             launch_diag_mode<1, 1, 3, 3>(dl, sink, mode, grid, stream);
             launch_diag_mode<1, 1, 6, 3>(dl, sink, mode, grid, stream);
             launches += 3;
-        }
+        }  // pairs with a d shell: the generic per-function diagonal kernel (fock_api.cu), then finish_diagonal
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        err = std::string("diagonal kernels: ") + cudaGetErrorString(e);
+        return -1;
+    }
+    return launches;
+}
+
+int ClassEngine::finish_diagonal(const double *d_diag, std::string &err) {
+    int launches = 0;
+    const size_t npairs = dev->meta_ints / 2;
+    for (size_t si = 0; si < sd->sublists.size(); ++si) {
+        const Sublist &s = sd->sublists[si];
+        const int n = (int)s.pair_ids.size();
+        if (!n || s.cls < 3) continue;
+        class_pairmax_kernel<<<(n + 127) / 128, 128, 0, stream>>>(d_meta_nat, dev->d_shell_bf, (int)(s.meta_off / 2), n, d_diag, d_maxdiag);
+        launches += 1;
     }
     // order every sublist by its pairs' maxima (descending) on the device -- non-negative doubles sort
     // like their bit patterns -- and permute the primitive-pair tables accordingly; the host only needs
@@ -251,7 +297,7 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
     plan.clear();
     plan_stats = ClassStats();
     // class pairs in a fixed order; within one, every (bra sublist >= ket sublist) job
-    for (int cb = 0; cb < 3; ++cb)
+    for (int cb = 0; cb < kNumPairClasses; ++cb)
         for (int ck = 0; ck <= cb; ++ck) {
             ClassPlanLaunch pl;
             pl.cb = cb;
@@ -261,7 +307,10 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
             // K-split threshold: one thread's primitive loop (class cost x depth, in instructions) may not
             // exceed a quarter of the average work per resident thread of this launch, nor ~6000
             // instructions when the launch is small -- otherwise it becomes the launch's critical path.
-            static const int kCost[3][3] = {{80, 0, 0}, {110, 200, 0}, {220, 600, 1000}};
+            // (rough instruction counts per primitive quartet; classes with a d shell scale with their flop model)
+            static const int kCost[6][6] = {{80, 0, 0, 0, 0, 0},          {110, 200, 0, 0, 0, 0},          {220, 600, 1000, 0, 0, 0},
+                                            {200, 400, 1500, 900, 0, 0}, {450, 1400, 4500, 3000, 9000, 0}, {1200, 3600, 12000, 8000, 24000, 60000}};
+            const bool reg_kernel = cb < 3 || kPairClassLA[cb] + kPairClassLB[cb] + kPairClassLA[ck] + kPairClassLB[ck] <= 5;
             double launch_work = 0.0;
             for (int b = 0; b < ns; ++b) {
                 const Sublist &sb = sd->sublists[b];
@@ -312,14 +361,14 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
                     // K-split: keep one thread's loop below ~6000 instructions (class cost x depth)
                     static const int kSplitMax = getenv("FOCK_KSPLIT_MAX") ? atoi(getenv("FOCK_KSPLIT_MAX")) : 32;
                     int S = 1;
-                    while (S < kSplitMax && 2 * S <= sk.K && (double)sb.K * sk.K * kCost[cb][ck] / S > loop_limit) S *= 2;
+                    while (reg_kernel && S < kSplitMax && 2 * S <= sk.K && (double)sb.K * sk.K * kCost[cb][ck] / S > loop_limit) S *= 2;
                     const long long per_tile = 32 / S;
                     const long long tiles = (quartets + per_tile - 1) / per_tile;
                     plan_stats.shell_quartets_total += (b == k) ? (long long)nb * (nb + 1) / 2 : (long long)nb * nk;
                     plan_stats.shell_quartets += quartets;
                     plan_stats.prim_quartets += quartets * (long long)sb.K * sk.K;
                     plan_stats.model_flops += (double)quartets * sb.K * sk.K *
-                                              model_flops_per_prim_quartet(kClsLA[cb], kClsLB[cb], kClsLA[ck], kClsLB[ck]);
+                                              model_flops_per_prim_quartet(kPairClassLA[cb], kPairClassLB[cb], kPairClassLA[ck], kPairClassLB[ck]);
                     plan_stats.warp_tiles += tiles;
                     if (tiles == 0) {
                         table.resize(off);
@@ -420,6 +469,8 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
         cl.njobs = pl.njobs;
         cl.total_tiles = pl.total_tiles;
         cl.shell_bf = dev->d_shell_bf;
+        cl.shell_scale = d_shell_scale;
+        cl.fix_r = (mode & FOCK_MODE_FIX_R_BIT) ? 1 : 0;
         cl.boys_poly = boys_poly;
         cl.boys_ni = boys_ni;
         cl.rank = plan_rank;
@@ -428,7 +479,20 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
         if (mine <= 0) continue;
         // persistent blocks: enough to fill the machine, each strides over the warp tiles
         dim3 grid((unsigned)std::min<long long>((mine + kClassWarps - 1) / kClassWarps, (long long)num_sms * kBlocksPerSm));
-        launches += launch_class(pl.cb, pl.ck, cl, sink, mode, grid, aux[slot % kStreams]);
+        int l = launch_class(pl.cb, pl.ck, cl, sink, mode, grid, aux[slot % kStreams]);
+        if (l == 0) {
+            // no register-resident kernel for this class pair (total angular momentum >= 6): one warp per
+            // quartet with shared-memory tables, driven by the same job / tile tables
+            if (!sq_shells) {
+                err = "class pair without a kernel and no shell-quartet tables";
+                return -1;
+            }
+            const SqEnv env{sq_shells, sq_exps, sq_coefs, sq_boys, mode, sq_tab};
+            const unsigned wgrid = (unsigned)std::min<long long>((mine + kSqWarps - 1) / kSqWarps, (long long)num_sms * 16);
+            eri_class_warpq_kernel<Sink><<<wgrid, kSqThreads, (size_t)kSqWarps * kSqSmemPerWarp * sizeof(double), aux[slot % kStreams]>>>(cl, env, sink);
+            l = 1;
+        }
+        launches += l;
         ++slot;
     }
     for (int i = 0; i < kAuxStreams; ++i) {
@@ -444,11 +508,11 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
 }
 
 template int ClassEngine::run_plan<TensorSink>(const TensorSink &, std::string &);
-template int ClassEngine::run_plan<DirectSink>(const DirectSink &, std::string &);
 template int ClassEngine::run_plan<BlockDirectSink>(const BlockDirectSink &, std::string &);
 
 ClassEngine::~ClassEngine() {
     if (d_table) cudaFree(d_table);
+    if (d_shell_scale) cudaFree(d_shell_scale);
     if (d_jobs) cudaFree(d_jobs);
     if (d_bra_nat) cudaFree(d_bra_nat);
     if (d_meta_nat) cudaFree(d_meta_nat);

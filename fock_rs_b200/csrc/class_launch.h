@@ -14,6 +14,19 @@ struct TensorSink;
 struct DirectSink;
 struct BlockDirectSink;
 struct ClassJob;
+struct ClassLaunch;
+struct SqShell;
+struct SqTables;
+
+// Register-resident class kernels for bra pair classes with a d shell (ds, dp, dd), total angular
+// momentum <= 5; one translation unit per (bra class, sink) so they compile in parallel
+// (dclass_*.cu).  Return the number of launches, 0 when the class pair has no such kernel.
+template <class Sink>
+int launch_dclass_ds(int ck, const ClassLaunch &cl, const Sink &sink, dim3 grid, cudaStream_t st);
+template <class Sink>
+int launch_dclass_dp(int ck, const ClassLaunch &cl, const Sink &sink, dim3 grid, cudaStream_t st);
+template <class Sink>
+int launch_dclass_dd(int ck, const ClassLaunch &cl, const Sink &sink, dim3 grid, cudaStream_t st);
 
 struct ClassStats {
     long long shell_quartets_total = 0;  // unique class shell quartets before screening
@@ -25,7 +38,7 @@ struct ClassStats {
 
 // One class-pair launch (all (bra sublist, ket sublist) jobs of one angular class pair).
 struct ClassPlanLaunch {
-    int cb = 0, ck = 0;       // pair classes 0 ss, 1 ps, 2 pp
+    int cb = 0, ck = 0;       // pair classes 0 ss, 1 ps, 2 pp, 3 ds, 4 dp, 5 dd
     int job_begin = 0, njobs = 0;
     long long total_tiles = 0;
 };
@@ -82,8 +95,17 @@ struct ClassEngine {
     cudaStream_t aux[kAuxStreams] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kAuxStreams] = {};
 
+    // warp-per-quartet fallback (classes without a register kernel): shell tables owned by SqState
+    const SqShell *sq_shells = nullptr;
+    const double *sq_exps = nullptr, *sq_coefs = nullptr;
+    BoysTables sq_boys{};
+    const SqTables *sq_tab = nullptr;
+    double *d_shell_scale = nullptr;  // [nshell][6]
+
     int upload_master(std::string &err);                 // once, after build_pairs
-    int run_diagonal(double *d_diag, std::string &err);  // returns launches or -1
+    int run_diagonal(double *d_diag, std::string &err);  // s/p diagonal blocks; returns launches or -1
+    // after every (xy|xy) is in d_diag: per-pair maxima of the d sublists, device sort, table permutation
+    int finish_diagonal(const double *d_diag, std::string &err);
     int sort_by_diagonal(std::string &err);  // uses h_maxdiag; returns launches or -1
     int make_plan(int screen, double thr, int rank, int world, std::string &err);
     template <class Sink>

@@ -1,0 +1,113 @@
+// dclass_dispatch.cuh -- launch tables of the register-resident class kernels whose bra pair holds a d
+// shell.  Every (bra class, sink) pair is instantiated in its own translation unit (dclass_*.cu) so that
+// the slices compile in parallel.  A class whose n_ab x n_cd component block exceeds ~18 accumulators
+// is covered by several SLICE launches ([CB0,CB0+CBN) x [KC0,KC0+KCN)), each recomputing the Boys values
+// and the R table of its primitive quartets (cheap next to the Hermite contractions of these classes).
+// Class pairs with total angular momentum >= 6 have no such kernel (their R table alone exceeds the
+// register file of one thread): the launchers return 0 and class_launch.cu falls back to the
+// warp-per-quartet kernel of eri_shellq.cuh.
+#pragma once
+#include <type_traits>
+
+#include "class_launch.h"
+#include "eri_class.cuh"
+
+namespace fock {
+
+template <int LA, int LB, int LC, int LD, int CB0, int CBN, int KC0, int KCN, class Sink>
+inline void launch_slice(const ClassLaunch &cl, const Sink &sink, dim3 grid, cudaStream_t st) {
+    const size_t smem = boys_smem_doubles(LA + LB + LC + LD, cl.boys_ni) * sizeof(double);
+    // FIXR = 2: the (t-1) factor of the R recursion is a run-time flag here (halves the instantiations)
+    eri_class_kernel<LA, LB, LC, LD, 2, CB0, CBN, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
+}
+
+// ket component slices [0, N) in steps of STEP, all bra components [CB0, CB0+CBN)
+template <int LA, int LB, int LC, int LD, int CB0, int CBN, int STEP, int KC0, class Sink>
+inline int launch_ket_slices(const ClassLaunch &cl, const Sink &sink, dim3 grid, cudaStream_t st) {
+    constexpr int NCD = ncart_c(LC) * ncart_c(LD);
+    if constexpr (KC0 < NCD) {
+        launch_slice<LA, LB, LC, LD, CB0, CBN, KC0, STEP>(cl, sink, grid, st);
+        return 1 + launch_ket_slices<LA, LB, LC, LD, CB0, CBN, STEP, KC0 + STEP>(cl, sink, grid, st);
+    } else {
+        return 0;
+    }
+}
+
+// ket component slices [KC0, KCEND) one at a time, bra components [CB0, CB0+CBN)
+template <int LA, int LB, int LC, int LD, int CB0, int CBN, int KC0, int KCEND, class Sink>
+inline int launch_ket_range(const ClassLaunch &cl, const Sink &sink, dim3 grid, cudaStream_t st) {
+    if constexpr (KC0 < KCEND) {
+        launch_slice<LA, LB, LC, LD, CB0, CBN, KC0, 1>(cl, sink, grid, st);
+        return 1 + launch_ket_range<LA, LB, LC, LD, CB0, CBN, KC0 + 1, KCEND>(cl, sink, grid, st);
+    } else {
+        return 0;
+    }
+}
+
+// Class pairs with total angular momentum 6..8, integral-direct sink only (dclass_hi_*.cu): with ONE ket
+// component per slice the compiler keeps only the sub-box of the R table that component reaches, so even
+// (dd|dd) stays in registers.  In-core builds of these classes use the warp-per-quartet fallback.
+int launch_hi_dpdp(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
+int launch_hi_ddpp(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
+int launch_hi_ddds(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
+int launch_hi_dddp_a(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
+int launch_hi_dddp_b(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
+int launch_hi_dddd_a(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
+int launch_hi_dddd_b(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
+int launch_hi_dddd_c(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
+int launch_hi_dddd_d(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
+
+#ifdef FOCK_DCLASS_DS
+template <class Sink>
+int launch_dclass_ds(int ck, const ClassLaunch &cl, const Sink &sink, dim3 grid, cudaStream_t st) {
+    switch (ck) {
+        case 0: return launch_ket_slices<2, 0, 0, 0, 0, 6, 1, 0>(cl, sink, grid, st);  // (ds|ss)  6 x 1
+        case 1: return launch_ket_slices<2, 0, 1, 0, 0, 6, 3, 0>(cl, sink, grid, st);  // (ds|ps)  6 x 3
+        case 2: return launch_ket_slices<2, 0, 1, 1, 0, 6, 3, 0>(cl, sink, grid, st);  // (ds|pp)  6 x 9 in 3 slices
+        case 3: return launch_ket_slices<2, 0, 2, 0, 0, 6, 3, 0>(cl, sink, grid, st);  // (ds|ds)  6 x 6 in 2 slices
+        default: return 0;
+    }
+}
+#endif
+
+#ifdef FOCK_DCLASS_DP
+template <class Sink>
+int launch_dclass_dp(int ck, const ClassLaunch &cl, const Sink &sink, dim3 grid, cudaStream_t st) {
+    switch (ck) {
+        case 0: return launch_ket_slices<2, 1, 0, 0, 0, 18, 1, 0>(cl, sink, grid, st);  // (dp|ss) 18 x 1
+        case 1: return launch_ket_slices<2, 1, 1, 0, 0, 18, 1, 0>(cl, sink, grid, st);  // (dp|ps) 18 x 3 in 3 slices
+        case 2: return launch_ket_slices<2, 1, 1, 1, 0, 18, 1, 0>(cl, sink, grid, st);  // (dp|pp) 18 x 9 in 9 slices
+        case 3: return launch_ket_slices<2, 1, 2, 0, 0, 18, 1, 0>(cl, sink, grid, st);  // (dp|ds) 18 x 6 in 6 slices
+        case 4:  // (dp|dp): L = 6, 18 x 18 in 18 slices
+            if constexpr (std::is_same<Sink, BlockDirectSink>::value) return launch_hi_dpdp(cl, sink, grid, st);
+            return 0;
+        default: return 0;
+    }
+}
+#endif
+
+#ifdef FOCK_DCLASS_DD
+template <class Sink>
+int launch_dclass_dd(int ck, const ClassLaunch &cl, const Sink &sink, dim3 grid, cudaStream_t st) {
+    switch (ck) {
+        case 0:  // (dd|ss) 36 x 1 in 2 bra slices
+            return launch_ket_slices<2, 2, 0, 0, 0, 18, 1, 0>(cl, sink, grid, st) +
+                   launch_ket_slices<2, 2, 0, 0, 18, 18, 1, 0>(cl, sink, grid, st);
+        case 1:  // (dd|ps) 36 x 3 in 6 slices
+            return launch_ket_slices<2, 2, 1, 0, 0, 18, 1, 0>(cl, sink, grid, st) +
+                   launch_ket_slices<2, 2, 1, 0, 18, 18, 1, 0>(cl, sink, grid, st);
+        default:  // (dd|pp), (dd|ds), (dd|dp), (dd|dd): L = 6, 6, 7, 8
+            if constexpr (std::is_same<Sink, BlockDirectSink>::value) {
+                if (ck == 2) return launch_hi_ddpp(cl, sink, grid, st);
+                if (ck == 3) return launch_hi_ddds(cl, sink, grid, st);
+                if (ck == 4) return launch_hi_dddp_a(cl, sink, grid, st) + launch_hi_dddp_b(cl, sink, grid, st);
+                if (ck == 5)
+                    return launch_hi_dddd_a(cl, sink, grid, st) + launch_hi_dddd_b(cl, sink, grid, st) +
+                           launch_hi_dddd_c(cl, sink, grid, st) + launch_hi_dddd_d(cl, sink, grid, st);
+            }
+            return 0;
+    }
+}
+#endif
+
+}  // namespace fock

@@ -1,0 +1,9 @@
+// dclass_hi_ddds.cu -- register-resident slice kernels of a class pair with total angular momentum >= 6
+// (integral-direct sink); see dclass_dispatch.cuh.
+#include "dclass_dispatch.cuh"
+
+namespace fock {
+int launch_hi_ddds(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st) {
+    return launch_ket_range<2, 2, 2, 0, 0, 18, 0, 6>(cl, sink, grid, st) + launch_ket_range<2, 2, 2, 0, 18, 18, 0, 6>(cl, sink, grid, st);
+}
+}  // namespace fock

@@ -44,7 +44,8 @@ void make_boys_table(std::vector<double> &tab) {
 struct ClassState {
     ClassEngine engine;
     ClassStats stats;
-    unsigned char *d_bf_class_ok = nullptr;  // function sits in an s/p class shell
+    unsigned char *d_bf_class_ok = nullptr;  // function sits in an s/p class shell (its diagonal comes from eri_diag_kernel)
+    bool all_sp_class = false;               // ... true for every function
     unsigned char *d_bf_covered = nullptr;   // function is handled by a shell-level path (class or shell-quartet kernel)
     bool all_covered = false;
     SqState sq;
@@ -208,6 +209,13 @@ int fock_create(const fock_basis *b, const fock_opts *opts_in, fock_ctx **out) {
             for (Shell &s : ctx->shells.shells) s.class_ok = false;
             ctx->shells.all_class_ok = false;
             ctx->shells.n_class_shells = 0;
+        } else if (o.kernel == 2) {  // d shells through the general warp-per-quartet list instead of the class engine
+            for (Shell &s : ctx->shells.shells)
+                if (s.L == 2) {
+                    s.class_ok = false;
+                    ctx->shells.all_class_ok = false;
+                    --ctx->shells.n_class_shells;
+                }
         }
         build_pairs(ctx->shells);
         ClassState *cs = &ctx->cs;
@@ -236,10 +244,17 @@ int fock_create(const fock_basis *b, const fock_opts *opts_in, fock_ctx **out) {
             ctx->err = err;
             return FOCK_ERR_CUDA;
         }
+        cs->engine.sq_shells = cs->sq.d_shells;
+        cs->engine.sq_exps = cs->sq.d_exps;
+        cs->engine.sq_coefs = cs->sq.d_coefs;
+        cs->engine.sq_boys = ctx->boys();
+        cs->engine.sq_tab = cs->sq.d_tab;
         cs->all_covered = true;
+        cs->all_sp_class = true;
         for (int i = 0; i < n; ++i) {
             const Shell &sh = ctx->shells.shells[ctx->shells.bf_shell[i]];
-            ok[i] = sh.class_ok ? 1 : 0;
+            ok[i] = (sh.class_ok && sh.L <= 1) ? 1 : 0;
+            if (!ok[i]) cs->all_sp_class = false;
             covered[i] = (o.kernel != 1 && sh.L <= 2) ? 1 : 0;
             if (!covered[i]) cs->all_covered = false;
         }
@@ -316,10 +331,18 @@ static int diagonal_launch(fock_ctx *ctx, int *launches) {
         }
         *launches += l;
     }
-    if (!ctx->shells.all_class_ok) {
+    if (!cs->all_sp_class) {  // function pairs outside the s/p class blocks (d shells, irregular shells, f/g functions)
         generic_diag_kernel<<<(unsigned)((ctx->npair + T - 1) / T), T, 0, st>>>(ctx->basis_dev(), ctx->boys(), ctx->opts.mode,
                                                                               cs->d_bf_class_ok, 1, ctx->npair, ctx->d_diag);
         *launches += 1;
+    }
+    if (!ctx->shells.pairs.empty()) {
+        const int l = cs->engine.finish_diagonal(ctx->d_diag, err);
+        if (l < 0) {
+            ctx->err = err;
+            return FOCK_ERR_CUDA;
+        }
+        *launches += l;
     }
     cs->sq.launch_pairmax(ctx->d_diag, st);
     FOCK_CUDA_TRY(ctx, cudaGetLastError());
@@ -607,28 +630,17 @@ int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev) {
         pack_density_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(D_dev, ctx->N, ctx->d_dvec, ctx->d_yvec, ctx->npair);
         // the class kernels digest shell blocks into the full matrix A (BlockDirectSink); the general paths
         // below still digest integral by integral into the packed y; combine_g_kernel adds the two
-        static const bool legacy_sink = getenv("FOCK_LEGACY_DIRECT_SINK") != nullptr;
         const unsigned nn_blocks = (unsigned)(((size_t)ctx->N * ctx->N + 255) / 256);
         symm_density_kernel<<<nn_blocks, 256, 0, st>>>(D_dev, ctx->N, ctx->d_Ds, ctx->d_A);
-        if (legacy_sink)
-            diag_digest_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(ctx->d_diag, ctx->npair, ctx->opts.rank,
-                                                                                   ctx->opts.world, ctx->d_dvec, ctx->d_yvec);
-        else
-            diag_digest_block_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(
-                ctx->d_diag, ctx->npair, ctx->opts.rank, ctx->opts.world, ctx->d_Ds, ctx->N, ctx->d_A);
+        diag_digest_block_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(ctx->d_diag, ctx->npair, ctx->opts.rank,
+                                                                                     ctx->opts.world, ctx->d_Ds, ctx->N, ctx->d_A);
         launches += 3;
         if (!ctx->shells.pairs.empty()) {
             std::string err;
             FOCK_TRY(make_plan_timed(ctx, thr, ctx->opts.rank, ctx->opts.world));
             FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_k0, st));
-            int l;
-            if (legacy_sink) {
-                DirectSink sink{ctx->d_yvec, ctx->d_dvec, ctx->d_diag, thr, ctx->opts.screen};
-                l = cs->engine.run_plan(sink, err);
-            } else {
-                BlockDirectSink sink{ctx->d_A, ctx->d_Ds, ctx->d_diag, thr, ctx->opts.screen, ctx->N};
-                l = cs->engine.run_plan(sink, err);
-            }
+            BlockDirectSink sink{ctx->d_A, ctx->d_Ds, ctx->d_diag, thr, ctx->opts.screen, ctx->N};
+            const int l = cs->engine.run_plan(sink, err);
             FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_k1, st));
             if (l < 0) {
                 ctx->err = err;

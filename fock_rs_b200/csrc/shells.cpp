@@ -9,11 +9,28 @@
 
 namespace fock {
 
+// one-dimensional Hermite table of a general record: { E^{ij}_t : i <= la, j <= lb, t <= i+j }, i-major
+static int e1d_count(int la, int lb) {
+    int n = 0;
+    for (int i = 0; i <= la; ++i)
+        for (int j = 0; j <= lb; ++j) n += i + j + 1;
+    return n;
+}
+static int e1d_off(int lb, int i, int j) {
+    int n = 0;
+    for (int ii = 0; ii < i; ++ii)
+        for (int jj = 0; jj <= lb; ++jj) n += ii + jj + 1;
+    for (int jj = 0; jj < j; ++jj) n += i + jj + 1;
+    return n;
+}
+
 int pair_fields(int cls) {
     switch (cls) {
         case 0: return 6;   // p Px Py Pz K (pad)
         case 1: return 8;   // p Px Py Pz KWx KWy KWz Kh
-        default: return 20; // p Px Py Pz KAB[3][3] KhA[3] KhB[3] Khh
+        case 2: return 20;  // p Px Py Pz KAB[3][3] KhA[3] KhB[3] Khh
+        default:            // pairs with a d shell: p Px Py Pz Ex[] Ey[] Ez[] (general record), padded to even
+            return (4 + 3 * e1d_count(kPairClassLA[cls], kPairClassLB[cls]) + 1) / 2 * 2;
     }
 }
 
@@ -64,7 +81,7 @@ bool build_shells(int n, const double *center, const int32_t *angular, const int
             if (ok) {
                 s.bf[comp] = f;
                 s.scale[comp] = ratio;
-                if (ratio != 1.0) s.class_ok = false;
+                if (ratio != 1.0 && s.L <= 1) s.class_ok = false;
                 out.bf_shell[f] = cur;
                 out.bf_comp[f] = comp;
                 joined = true;
@@ -110,7 +127,7 @@ void build_pairs(ShellData &sd) {
             ShellPair p;
             p.A = A;
             p.B = B;
-            p.cls = sd.shells[A].L + sd.shells[B].L;  // 0 ss, 1 ps, 2 pp  (L <= 1)
+            p.cls = pair_class(sd.shells[A].L, sd.shells[B].L);
             p.K = sd.shells[A].nprim * sd.shells[B].nprim;
             sd.pairs.push_back(p);
         }
@@ -165,6 +182,31 @@ static void fill_record(const ShellData &sd, const ShellPair &pr, int i, int j, 
     const double K = ca * cb * e00 * kSqrtPref / p;
     rec[0] = p;
     for (int k = 0; k < 3; ++k) rec[1 + k] = (a * A.c[k] + b * B.c[k]) / p;
+    if (pr.cls >= 3) {
+        // general record: the one-dimensional tables E^{ij}_t of basis/src/utils.rs:33-50 (i lowered while
+        // j = 0, then j), the x table carrying c_a c_b sqrt(2 pi^{5/2}) / p
+        const int la = A.L, lb = B.L, cnt = e1d_count(la, lb);
+        const double half_ip = 1.0 / (2.0 * p);
+        for (int dim = 0; dim < 3; ++dim) {
+            double E[3][3][5] = {};
+            const double fa = q * X[dim] / a, fb = q * X[dim] / b;
+            E[0][0][0] = std::exp(-q * (X[dim] * X[dim])) * (dim == 0 ? ca * cb * kSqrtPref / p : 1.0);
+            for (int i = 1; i <= la; ++i)
+                for (int t = 0; t <= i; ++t)
+                    E[i][0][t] = half_ip * (t > 0 ? E[i - 1][0][t - 1] : 0.0) - fa * E[i - 1][0][t] +
+                                 (t + 1 <= i - 1 ? (double)(t + 1) * E[i - 1][0][t + 1] : 0.0);
+            for (int i = 0; i <= la; ++i)
+                for (int j = 1; j <= lb; ++j)
+                    for (int t = 0; t <= i + j; ++t)
+                        E[i][j][t] = half_ip * (t > 0 ? E[i][j - 1][t - 1] : 0.0) + fb * E[i][j - 1][t] +
+                                     (t + 1 <= i + j - 1 ? (double)(t + 1) * E[i][j - 1][t + 1] : 0.0);
+            for (int i = 0; i <= la; ++i)
+                for (int j = 0; j <= lb; ++j)
+                    for (int t = 0; t <= i + j; ++t) rec[4 + dim * cnt + e1d_off(lb, i, j) + t] = E[i][j][t];
+        }
+        if ((4 + 3 * cnt) & 1) rec[4 + 3 * cnt] = 0.0;
+        return;
+    }
     if (pr.cls == 0) {
         rec[4] = K;
         rec[5] = 0.0;
@@ -206,7 +248,7 @@ void build_pair_tables(ShellData &sd, std::vector<double> &bra, std::vector<doub
     bra.assign(bra_n, 0.0);
     ket.assign(ket_n, 0.0);
     meta.assign(meta_n, 0);
-    std::vector<double> rec(32);
+    std::vector<double> rec(96);
     for (const Sublist &s : sd.sublists) {
         for (size_t pi = 0; pi < s.pair_ids.size(); ++pi) {
             const ShellPair &pr = sd.pairs[s.pair_ids[pi]];

@@ -13,8 +13,11 @@
 
 namespace fock {
 
-constexpr int kMaxClassL = 1;  // class kernels cover s and p shells; the rest goes to the generic kernel
-constexpr int kNumPairClasses = 3;  // ss, ps, pp
+constexpr int kMaxClassL = 2;  // class kernels cover s, p and d shells; the rest goes to the generic kernel
+constexpr int kNumPairClasses = 6;  // ss, ps, pp, ds, dp, dd
+// pair class of shells with angular momenta la >= lb
+inline int pair_class(int la, int lb) { return la * (la + 1) / 2 + lb; }
+constexpr int kPairClassLA[kNumPairClasses] = {0, 1, 1, 2, 2, 2}, kPairClassLB[kNumPairClasses] = {0, 0, 1, 0, 1, 2};
 
 inline int ncart(int L) { return (L + 1) * (L + 2) / 2; }
 
@@ -33,12 +36,12 @@ struct Shell {
     int prim_begin = 0;  // into ShellData::exps / coefs (radial coefficients, norm of component 0 folded in)
     int bf[6] = {-1, -1, -1, -1, -1, -1};  // basis-function index of each Cartesian component (-1 = absent)
     double scale[6] = {1, 1, 1, 1, 1, 1};  // coefficient list of component c = scale[c] * radial list
-    bool class_ok = false;  // eligible for the class kernels (L <= kMaxClassL, unit component scales)
+    bool class_ok = false;  // eligible for the class kernels (L <= kMaxClassL; s and p need unit component scales)
 };
 
 struct ShellPair {
     int A = 0, B = 0;    // shell ids, (L_A, A) >= (L_B, B)
-    int cls = 0;         // 0 ss, 1 ps, 2 pp
+    int cls = 0;         // 0 ss, 1 ps, 2 pp, 3 ds, 4 dp, 5 dd
     int K = 0;           // nprim_A * nprim_B
     double maxdiag = 0;  // max over components of the basis-function diagonal (xy|xy)
 };
@@ -75,7 +78,7 @@ struct PairTablesDev {
     size_t bra_doubles = 0, ket_doubles = 0, meta_ints = 0;
 };
 
-// Doubles per primitive pair for pair class cls (0 ss, 1 ps, 2 pp); layout in pairs.cpp.
+// Doubles per primitive pair for pair class cls; layouts in shells.cpp (fill_record) / eri_class.cuh.
 int pair_fields(int cls);
 
 // Build shells from the flat basis.  Returns false with `err` set on malformed input.

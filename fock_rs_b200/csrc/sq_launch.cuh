@@ -34,6 +34,7 @@ struct SqState {
     std::vector<int> g_nat;  // [nG][2] shell ids, natural order
     std::vector<int> c_pair_ids;  // indices into ShellData::pairs
     SqShell *d_shells = nullptr;
+    SqTables *d_tab = nullptr;
     double *d_exps = nullptr, *d_coefs = nullptr;
     int *d_gmeta_nat = nullptr;
     double *d_gmax = nullptr, *h_gmax = nullptr;
@@ -43,7 +44,7 @@ struct SqState {
     SqLaunch launch{};
 
     void destroy() {
-        void *dp[] = {d_shells, d_exps, d_coefs, d_gmeta_nat, d_gmax, d_meta, d_prefix};
+        void *dp[] = {d_shells, d_tab, d_exps, d_coefs, d_gmeta_nat, d_gmax, d_meta, d_prefix};
         for (void *p : dp)
             if (p) cudaFree(p);
         void *hp[] = {h_gmax, h_meta, h_prefix};
@@ -56,12 +57,14 @@ struct SqState {
     int init(const ShellData &sd, std::string &err) {
         const int ns = (int)sd.shells.size();
         std::vector<int> eligible(ns);
-        bool any_nonclass = false;
+        bool any_nonclass = false, any_d = false;
         for (int s = 0; s < ns; ++s) {
             eligible[s] = sd.shells[s].L <= 2;
             if (eligible[s] && !sd.shells[s].class_ok) any_nonclass = true;
+            if (sd.shells[s].L == 2) any_d = true;
         }
-        if (!any_nonclass) return 0;
+        // the shell tables also serve the class engine's warp-per-quartet fallback (d classes with L >= 6)
+        if (!any_nonclass && !any_d) return 0;
         for (int a = 0; a < ns; ++a)
             for (int b = 0; b <= a; ++b)
                 if (eligible[a] && eligible[b] && !(sd.shells[a].class_ok && sd.shells[b].class_ok)) {
@@ -98,7 +101,8 @@ struct SqState {
                 }
         cudaError_t ce;
         const size_t npairs = (size_t)nG + nC;
-        if ((ce = cudaMemcpyToSymbol(c_sq, &tab, sizeof(tab))) != cudaSuccess ||
+        if ((ce = cudaMalloc((void **)&d_tab, sizeof(tab))) != cudaSuccess ||
+            (ce = cudaMemcpy(d_tab, &tab, sizeof(tab), cudaMemcpyHostToDevice)) != cudaSuccess ||
             (ce = cudaMalloc((void **)&d_shells, hs.size() * sizeof(SqShell))) != cudaSuccess ||
             (ce = cudaMalloc((void **)&d_exps, sd.exps.size() * sizeof(double) + 8)) != cudaSuccess ||
             (ce = cudaMalloc((void **)&d_coefs, sd.coefs.size() * sizeof(double) + 8)) != cudaSuccess ||
@@ -116,7 +120,7 @@ struct SqState {
         cudaMemcpy(d_exps, sd.exps.data(), sd.exps.size() * sizeof(double), cudaMemcpyHostToDevice);
         cudaMemcpy(d_coefs, sd.coefs.data(), sd.coefs.size() * sizeof(double), cudaMemcpyHostToDevice);
         cudaMemcpy(d_gmeta_nat, g_nat.data(), g_nat.size() * sizeof(int), cudaMemcpyHostToDevice);
-        enabled = true;
+        enabled = nG > 0;
         return 0;
     }
 
@@ -177,6 +181,7 @@ struct SqState {
         launch.exps = d_exps;
         launch.coefs = d_coefs;
         launch.boys = boys;
+        launch.tab = d_tab;
         launch.mode = mode;
         launch.rank = rank;
         launch.world = world;

@@ -267,7 +267,7 @@ __global__ void boys_poly_batch_kernel(const double *__restrict__ poly, int ni, 
                                        int order, double *__restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    double F0[1], F1[2], F2[3], F3[4], F4[5];
+    double F0[1], F1[2];
     // global-memory table with the shared-memory layout of the order requested
     switch (order) {
         case 0: boys_poly_eval<0>(T[i], F0, poly, ni); out[i] = F0[0]; break;
@@ -284,10 +284,11 @@ __global__ void boys_poly_batch_kernel(const double *__restrict__ poly, int ni, 
                 double r = c[7 * ni];
                 for (int j = 6; j >= 0; --j) r = fma(r, x, c[j * ni]);
                 out[i] = r;
-            } else {
-                if (L == 2) { boys_poly_eval<2>(t, F2, poly, ni); out[i] = F2[2]; }
-                else if (L == 3) { boys_poly_eval<3>(t, F3, poly, ni); out[i] = F3[3]; }
-                else { boys_poly_eval<4>(t, F4, poly, ni); out[i] = F4[4]; }
+            } else {  // asymptotic form, boys/src/lib.rs:65-68
+                const double r = rsqrt(t), h = 0.5 * r * r;
+                double f = 0.88622692545275801364908374167057 * r;
+                for (int m = 1; m <= L; ++m) f *= (double)(2 * m - 1) * h;
+                out[i] = f;
             }
         }
     }

@@ -81,7 +81,8 @@ typedef struct {
     int32_t rank;     /* this process's shard of the shell-quartet tiles, 0 <= rank < world */
     int32_t world;    /* number of shards (1 = whole job) */
     int32_t keep_eri; /* in-core: also keep the raw (ij|kl) tensor for fock_eri_get/export (default 1) */
-    int32_t kernel;   /* 0 = class kernels (default), 1 = force the generic per-function kernel */
+    int32_t kernel;   /* 0 = class kernels (default), 1 = force the generic per-function kernel,
+                       * 2 = class kernels for s/p shells only, d shells through the general shell-quartet kernel */
     int32_t incore_shard; /* world > 1, in-core: 0 = replicate the build, shard the per-iteration streaming
                              (best when a build is followed by more than ~T_build/T_G iterations);
                              1 = shard the build, every rank streams its own partial supermatrix */
@@ -162,7 +163,7 @@ int fock_timings(fock_ctx *ctx, double *ms, int32_t n);
  *   [6] kernel launches of the last fock_eri_build  [7] kernel launches of the last fock_build_g
  *   [8] model FP64 flops of the class quartets evaluated (SURVEY.md section 8d formula)
  *   [9] integrals evaluated by the per-function generic kernel  [10] warp tiles of the class launches
- *   [11] shell quartets evaluated by the general (d-capable) shell-quartet kernel */
+ *   [11] shell quartets evaluated by the general shell-quartet kernel (irregular shells; d shells with kernel = 2) */
 int fock_stats(fock_ctx *ctx, int64_t *out, int32_t n);
 
 /* Measurement aid (no reference counterpart): sustained FP64 FMA rate of this GPU from a

@@ -281,24 +281,26 @@ def test_device_boys_function_matches_reference(mode, exact):
 
 @pytest.mark.parametrize("mode,oflags", MODES)
 @pytest.mark.parametrize("mol,basis", [("water", "6-31G**"), ("ethene", "6-31G**")])
-def test_d_shell_quartets_through_shell_quartet_kernel(mol, basis, mode, oflags):
-    """Cartesian d shells (total L up to 8, Boys order up to 8) go through the general shell-quartet
-    kernel; tensor, G (in-core and direct) against the oracle."""
+@pytest.mark.parametrize("kernel", [0, 2])
+def test_d_shell_quartets(mol, basis, mode, oflags, kernel):
+    """Cartesian d shells (total L up to 8, Boys order up to 8): kernel 0 = the class engine (register-
+    resident slice kernels, warp-per-quartet fallback for in-core builds of L >= 6 classes), kernel 2 = the
+    general shell-quartet list; tensor, G (in-core and direct) against the oracle."""
     fb = flat_for(mol, basis)
     ob = oracle.OracleBasis.from_flat(fb)
     want, _ = oracle.from_basis_packed(ob, oflags, fast=True)
     D = random_symmetric_density(fb.n_basis, seed=12)
-    with FockBuilder(fb, mode=mode) as b:
+    with FockBuilder(fb, mode=mode, kernel=kernel) as b:
         b.eri_build()
         got = b.eri_export_packed()
         G = b.build_g(D)
         st = b.stats()
-    assert st["general_shell_quartets_evaluated"] > 0 and st["generic_integrals_evaluated"] == 0
+    assert (st["general_shell_quartets_evaluated"] > 0) == (kernel == 2) and st["generic_integrals_evaluated"] == 0
     assert np.max(np.abs(got - want)) <= ERI_TOL
     assert_same_cut(got, want)
     G_want = oracle.build_g(want, fb.n_basis, D)
     assert np.max(np.abs(G - G_want)) <= G_TOL
-    with FockBuilder(fb, mode=mode, storage=_lib.STORAGE_DIRECT) as b:
+    with FockBuilder(fb, mode=mode, storage=_lib.STORAGE_DIRECT, kernel=kernel) as b:
         Gd = b.eri_build().build_g(D)
     assert np.max(np.abs(Gd - G_want)) <= G_TOL
 
