@@ -379,7 +379,7 @@ def run_ours(args):
     others = []
     if not args.no_other_configs:
         # all ranks take part (sharded runs); rank 0 reports
-        for wl, stor in (("benzene", "incore"), ("w16", "incore"), ("alkane40", "direct")):
+        for wl, stor in (("benzene", "incore"), ("w16", "incore"), ("alkane40", "direct"), ("w32", "direct")):
             if (wl, stor) != (args.workload, args.storage):
                 others.append(quick_config(wl, stor, "ref", rank, world, local, incore_shard=1 if args.incore_shard == "build" else 0))
     if rank == 0:
@@ -394,7 +394,8 @@ def run_ours(args):
         if direct:
             dominant = "class_kernels (inside the fused G build)"
         roof_eri = {"bound": "fp64", "achieved": eri_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": eri_tf / fp64_peak if fp64_peak else None,
-                    "traffic": None, "kernel": "eri_class_kernel<*> (the 8 class launches of one build, CUDA events around them)",
+                    "traffic": ncu_traffic(args.workload, storage == _lib.STORAGE_DIRECT),
+                    "kernel": "eri_class_kernel<*> (all class / slice launches of one build, CUDA events around them)",
                     "note": "model flops of the quartets evaluated (SURVEY.md 8d formula) / time between the events bracketing the class launches; peak = DFMA-chain probe measured in this run"}
         # DRAM bytes of one symv launch from the committed ncu --set full capture (profiles/r01_*_ncu_full_w16_refcut.md)
         symv_traffic = 1.894e9 if (args.workload == "w16" and world == 1 and storage == _lib.STORAGE_INCORE) else None
@@ -405,7 +406,7 @@ def run_ours(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, flat),
             "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "shell_quartets/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 8 * n * n, "d2h_bytes_per_step": 8 * n * n},
-            "gpu_launches": int((st["launches_build"] + st["launches_g"]) * args.steps),
+            "gpu_launches": int((st["launches_g"] if direct else st["launches_build"] + st["launches_g"]) * args.steps),
             "clocks": clocks.summary(),
             "roofline": roof_g if (dominant == "g_ms" and storage == _lib.STORAGE_INCORE) else roof_eri,
             "roofline_eri": roof_eri, "roofline_digest": roof_g if storage == _lib.STORAGE_INCORE else None,
@@ -422,6 +423,17 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic(workload, direct):
+    """DRAM bytes (read + write) per launch of the heaviest class kernel of this workload, from the committed
+    `ncu --set full` capture (profiles/ncu_traffic.json, written by tools/summarize_ncu.py); None if no
+    capture of this workload is on file.  These kernels are FP64-bound: the traffic is megabytes."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f).get(workload + ("/direct" if direct else "/incore"), {}).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        return None
 
 
 def quick_config(workload, storage, screen, rank, world, local, steps=5, incore_shard=1):
