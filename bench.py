@@ -33,6 +33,7 @@ WORKLOADS = {
     "w16": ("(H2O)16 water cluster 6-31G (208 bf)", "w16", "6-31G"),
     "alkane40": ("Linear alkane C40H82 6-31G (524 bf)", "alkane40", "6-31G"),
     "w32": ("(H2O)32 6-31G** (800 bf Cartesian)", "w32", "6-31G**"),
+    "w32cc": ("(H2O)32 cc-pVDZ-shaped synthetic set, general contraction (800 bf Cartesian)", "w32", "cc-pVDZ"),
     "water": ("H2O RHF STO-3G (7 bf)", "water", "STO-3G"),
 }
 
@@ -379,7 +380,7 @@ def run_ours(args):
     others = []
     if not args.no_other_configs:
         # all ranks take part (sharded runs); rank 0 reports
-        for wl, stor in (("benzene", "incore"), ("w16", "incore"), ("alkane40", "direct"), ("w32", "direct")):
+        for wl, stor in (("benzene", "incore"), ("w16", "incore"), ("alkane40", "direct"), ("w32", "direct"), ("w32cc", "direct")):
             if (wl, stor) != (args.workload, args.storage):
                 others.append(quick_config(wl, stor, "ref", rank, world, local, incore_shard=1 if args.incore_shard == "build" else 0))
     if rank == 0:
@@ -416,6 +417,8 @@ def run_ours(args):
             "fp64_peak_tflops_measured": fp64_peak,
         }
         line["other_configs"] = others
+        if world == 1 and not args.no_other_configs:
+            line["orbital_voxelizer"] = voxel_config(local, with_cpu=not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.workload, args.screen == "ref", args.cpu_budget, nq).items() if k not in ("checksum",)}
         print(json.dumps(line))
@@ -423,6 +426,42 @@ def run_ours(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def voxel_config(local, with_cpu=True):
+    """SURVEY 8 row f4, reported beside the headline: the volumetric renderer's 200^3 x 20 bohr grid
+    (volumetric/src/main.rs:63-64,100-125) for one benzene/6-31G orbital through fock_orbital_voxelize
+    (host buffer out), and the oracle's restatement of the reference loop on a bounded slab of the same grid."""
+    from fock_rs_b200.fock import FockBuilder
+
+    flat = load_flat("benzene")
+    rng = np.random.default_rng(20261017)
+    c = rng.uniform(-1.0, 1.0, flat.n_basis)
+    nv, box = 200, 20.0
+    with FockBuilder(flat, device=local) as b:
+        b.orbital_voxelize(c, nv, box)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            grid = b.orbital_voxelize(c, nv, box)
+        e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+        st = b.orbital_stats()
+    nprim = int(sum(flat.prim_offset[i + 1] - flat.prim_offset[i] for i in range(flat.n_basis) if abs(c[i]) > 0.05))
+    out = {"workload": "benzene/6-31G orbital on the renderer's 200^3 voxel grid (box 20 bohr)", "voxels": nv ** 3, "functions": st["functions"],
+           "exp_groups": st["groups"], "kernel_ms": st["kernel_ms"], "e2e_ms_host_grid_out": e2e_ms, "d2h_bytes": 4 * nv ** 3,
+           "voxels_per_s": nv ** 3 / (st["kernel_ms"] * 1e-3), "reference_primitive_terms_per_s": nprim * nv ** 3 / (st["kernel_ms"] * 1e-3)}
+    if with_cpu:
+        import oracle
+
+        ob = oracle.OracleBasis.from_flat(flat)
+        planes = 4
+        lo = 98 * nv * nv
+        t0 = time.perf_counter()
+        ref = oracle.voxelize(ob, c, nv, box, begin=lo, end=lo + planes * nv * nv)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"kind": "port", "cores": oracle.num_threads(), "sample": f"{planes} of {nv} z-planes", "sample_s": dt,
+                               "whole_grid_s_extrapolated": dt * nv / planes, "max_abs_diff_vs_gpu": float(np.max(np.abs(ref - grid[lo:lo + planes * nv * nv])))}
+    return out
 
 
 def ncu_traffic(workload, direct):
@@ -510,7 +549,7 @@ def main():
     ap.add_argument("--no-other-configs", action="store_true", help="skip the secondary workloads reported in other_configs")
     args = ap.parse_args()
     if args.storage is None:
-        args.storage = "direct" if args.workload in ("alkane40", "w32") else "incore"
+        args.storage = "direct" if args.workload in ("alkane40", "w32", "w32cc") else "incore"
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -25,6 +25,7 @@ EXPORTS = [
     "fock_eri_batch", "fock_build_g", "fock_build_g_device", "fock_one_electron", "fock_set_stream",
     "fock_supermatrix_device", "fock_set_digest_range", "fock_timings", "fock_stats", "fock_last_error", "fock_destroy",
     "fock_abi_version", "fock_measure_fp64_peak", "fock_boys_batch",
+    "fock_orbital_eval", "fock_orbital_voxelize", "fock_orbital_stats",
 ]
 
 
@@ -99,5 +100,8 @@ def load():
     L.fock_abi_version.restype = C.c_int
     L.fock_measure_fp64_peak.argtypes = [vp, dp]
     L.fock_boys_batch.argtypes = [vp, dp, C.c_size_t, C.c_int32, dp]
+    L.fock_orbital_eval.argtypes = [vp, dp, C.c_double, dp, C.c_size_t, dp]
+    L.fock_orbital_voxelize.argtypes = [vp, dp, C.c_double, C.c_int32, C.c_double, C.POINTER(C.c_float)]
+    L.fock_orbital_stats.argtypes = [vp, dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     _lib = L
     return L

@@ -92,22 +92,30 @@ class Atom:
 class BasisSet:
     """MolSSI BSE JSON basis set (basis_set/src/lib.rs:62-76) + `get` (:79-118)."""
 
-    def __init__(self, doc: dict):
+    def __init__(self, doc: dict, general_contraction: bool = False):
         self.doc = doc
+        # False (default) = the reference's `get`: function set `idx` of a shell uses `coefficients[idx]` with idx
+        # enumerating `angular_momentum` (basis_set/src/lib.rs:86,107), so the extra columns of a generally
+        # contracted shell (one angular momentum, several coefficient columns) are silently dropped.
+        # True = SURVEY 8 row f2: every column of such a shell becomes its own contracted function set and
+        # primitives whose coefficient is exactly zero (BSE pads general contractions with zeros) are left out.
+        self.general_contraction = bool(general_contraction)
         self.name = doc.get("name", "?")
         self.elements = {int(z): e for z, e in doc["elements"].items()}
 
     @classmethod
-    def from_file(cls, path: str) -> "BasisSet":
+    def from_file(cls, path: str, general_contraction: bool = False) -> "BasisSet":
         with open(path) as f:
-            return cls(json.load(f))
+            return cls(json.load(f), general_contraction)
 
     @classmethod
-    def named(cls, name: str) -> "BasisSet":
+    def named(cls, name: str, general_contraction: bool = False) -> "BasisSet":
         """Shipped sets (trimmed copies of the reference's basis_set/src/data/*.json,
-        basis_sets.rs:12-24): 'STO-3G', 'STO-6G', '3-21G', '6-31G', '6-31G*', '6-31G**', '6-311G'."""
+        basis_sets.rs:12-24): 'STO-3G', 'STO-6G', '3-21G', '6-31G', '6-31G*', '6-31G**', '6-311G'; plus
+        'cc-pVDZ', a cc-pVDZ-SHAPED synthetic set for H and O (generally contracted; see its
+        revision_description and SURVEY.md App. D) that needs `general_contraction=True` to load in full."""
         fname = name.replace("**", "_st_st").replace("*", "_st") + ".json"
-        return cls.from_file(os.path.join(_DATA, fname))
+        return cls.from_file(os.path.join(_DATA, fname), general_contraction)
 
     def get(self, position, atom_type: int) -> Atom:
         config = self.elements.get(int(atom_type))
@@ -116,7 +124,11 @@ class BasisSet:
         position = tuple(float(x) for x in position)
         functions: List[ContractedGaussian] = []
         for shell in config["electron_shells"]:
-            for idx, angular in enumerate(shell["angular_momentum"]):
+            columns = list(enumerate(shell["angular_momentum"]))
+            general = self.general_contraction and len(shell["angular_momentum"]) == 1 and len(shell["coefficients"]) > 1
+            if general:
+                columns = [(idx, shell["angular_momentum"][0]) for idx in range(len(shell["coefficients"]))]
+            for idx, angular in columns:
                 angulars = [
                     (x, y, z)
                     for x in range(angular + 1)
@@ -127,7 +139,8 @@ class BasisSet:
                 coeffs = shell["coefficients"][idx]
                 for ang in angulars:
                     # zip() truncates to the shorter list exactly like Iterator::zip
-                    prims = [GaussianPrimitive.new(ang, float(e), float(c)) for e, c in zip(shell["exponents"], coeffs)]
+                    prims = [GaussianPrimitive.new(ang, float(e), float(c)) for e, c in zip(shell["exponents"], coeffs)
+                             if not (general and float(c) == 0.0)]
                     functions.append(ContractedGaussian(position, prims))
         return Atom(position, int(atom_type), functions)
 

@@ -48,6 +48,8 @@ struct fock_ctx {
     double timings[8]{};
     int64_t stats[16]{};
     size_t digest_begin = 0, digest_end = 0;
+    double orbital_ms = 0.0;  // last fock_orbital_voxelize kernel time
+    int orbital_functions = 0, orbital_groups = 0;
     bool built = false;
     int device = 0;
     std::string err;

@@ -134,6 +134,33 @@ class FockBuilder:
         self._check(self._L.fock_one_electron(self._ctx, pos.shape[0], _dp(pos), _dp(chg), _dp(S), _dp(T), _dp(V)))
         return S, T, V
 
+    def orbital_eval(self, coeff, points, min_coeff: float = 0.05) -> np.ndarray:
+        """`MolecularOrbital::evaluate` (scf/src/molecular_orbitals.rs:37-43) for one coefficient column at a
+        batch of points; functions with |coeff| <= min_coeff are dropped as `MolecularOrbitals::new` does."""
+        c = np.ascontiguousarray(coeff, dtype=np.float64)
+        if c.shape != (self.n,):
+            raise ValueError("coeff must have N entries")
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        out = np.empty(pts.shape[0], dtype=np.float64)
+        self._check(self._L.fock_orbital_eval(self._ctx, _dp(c), float(min_coeff), _dp(pts), pts.shape[0], _dp(out)))
+        return out
+
+    def orbital_voxelize(self, coeff, n_voxels: int = 200, box_size: float = 20.0, min_coeff: float = 0.05) -> np.ndarray:
+        """`State::create_wave_texture_data` (volumetric/src/main.rs:100-125): psi on the n^3 voxel grid as
+        f32, x fastest (flat, exactly the R32F texture image the renderer uploads)."""
+        c = np.ascontiguousarray(coeff, dtype=np.float64)
+        if c.shape != (self.n,):
+            raise ValueError("coeff must have N entries")
+        out = np.empty(int(n_voxels) ** 3, dtype=np.float32)
+        self._check(self._L.fock_orbital_voxelize(self._ctx, _dp(c), float(min_coeff), int(n_voxels), float(box_size),
+                                                  out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def orbital_stats(self) -> dict:
+        ms, nf, ng = C.c_double(), C.c_int32(), C.c_int32()
+        self._check(self._L.fock_orbital_stats(self._ctx, C.byref(ms), C.byref(nf), C.byref(ng)))
+        return {"kernel_ms": ms.value, "functions": nf.value, "groups": ng.value}
+
     def set_stream(self, stream_ptr: Optional[int]):
         self._check(self._L.fock_set_stream(self._ctx, C.c_void_p(stream_ptr or 0)))
 
@@ -165,6 +192,38 @@ class FockBuilder:
             "shell_quartets_evaluated": s[4], "prim_quartets_evaluated": s[5], "launches_build": s[6],
             "launches_g": s[7], "model_flops": s[8], "generic_integrals_evaluated": s[9], "warp_tiles": s[10], "general_shell_quartets_evaluated": s[11],
         }
+
+
+class MolecularOrbitals:
+    """Host mirror of `scf::molecular_orbitals::MolecularOrbitals` (scf/src/molecular_orbitals.rs:6-100):
+    `orbitals[n].evaluate(at)` and the volumetric renderer's voxel grid, evaluated on the device."""
+
+    MIN_COEFFICIENT_MAGNITUDE = 0.05  # molecular_orbitals.rs:47
+
+    class _Orbital:
+        def __init__(self, owner, column):
+            self._o, self._c = owner, column
+
+        def evaluate(self, at) -> float:
+            return float(self._o._b.orbital_eval(self._c, np.asarray(at, dtype=np.float64).reshape(1, 3), self._o.MIN_COEFFICIENT_MAGNITUDE)[0])
+
+        def evaluate_many(self, points) -> np.ndarray:
+            return self._o._b.orbital_eval(self._c, points, self._o.MIN_COEFFICIENT_MAGNITUDE)
+
+        def voxelize(self, n_voxels: int = 200, box_size: float = 20.0) -> np.ndarray:
+            return self._o._b.orbital_voxelize(self._c, n_voxels, box_size, self._o.MIN_COEFFICIENT_MAGNITUDE)
+
+    def __init__(self, basis, coeff_matrix, builder: Optional[FockBuilder] = None, **opts):
+        self._b = builder if builder is not None else FockBuilder(basis, **opts)
+        self._C = np.asarray(coeff_matrix, dtype=np.float64)
+        if self._C.shape != (self._b.n, self._b.n):
+            raise ValueError("coefficient matrix must be N x N")
+
+    def __len__(self):
+        return self._C.shape[1]
+
+    def __getitem__(self, n: int) -> "MolecularOrbitals._Orbital":
+        return MolecularOrbitals._Orbital(self, np.ascontiguousarray(self._C[:, n]))
 
 
 class ElectronTensor:

@@ -92,6 +92,22 @@ class FockBuilder {
         check(fock_build_g(ctx_, density.data(), g.data()));
         return g;
     }
+    // MolecularOrbital::evaluate (scf/src/molecular_orbitals.rs:37-43) for one coefficient column at `points`
+    // ([n][3], bohr); |coeff| <= min_coeff dropped as MolecularOrbitals::new does (:70-79).
+    std::vector<double> orbital_eval(const std::vector<double> &coeff, const std::vector<double> &points, double min_coeff = 0.05) const {
+        if ((int)coeff.size() != n_ || points.size() % 3) throw FockError(FOCK_ERR_BAD_ARG, "coeff must be N, points [n][3]");
+        std::vector<double> v(points.size() / 3);
+        check(fock_orbital_eval(ctx_, coeff.data(), min_coeff, points.data(), v.size(), v.data()));
+        return v;
+    }
+    // State::create_wave_texture_data (volumetric/src/main.rs:100-125): n^3 f32 voxels, x fastest
+    std::vector<float> orbital_voxelize(const std::vector<double> &coeff, int n_voxels = 200, double box_size = 20.0,
+                                        double min_coeff = 0.05) const {
+        if ((int)coeff.size() != n_) throw FockError(FOCK_ERR_BAD_ARG, "coeff must be N");
+        std::vector<float> g((size_t)n_voxels * n_voxels * n_voxels);
+        check(fock_orbital_voxelize(ctx_, coeff.data(), min_coeff, n_voxels, box_size, g.data()));
+        return g;
+    }
     fock_ctx *raw() const { return ctx_; }
 
    private:

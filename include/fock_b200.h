@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FOCK_B200_ABI_VERSION 2
+#define FOCK_B200_ABI_VERSION 3
 
 typedef struct fock_ctx fock_ctx;
 
@@ -136,6 +136,23 @@ int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev);
  * `nuclei_pos[n][3]`, `nuclei_charge[n]` = PointCharge (basis/src/lib.rs:8-12). */
 int fock_one_electron(fock_ctx *ctx, int32_t n_nuclei, const double *nuclei_pos, const double *nuclei_charge,
                       double *S, double *T, double *V);
+
+/* Molecular-orbital evaluation (the renderers' hot loop).
+ *   psi(at) = sum_f coeff[f] * chi_f(at)         MolecularOrbital::evaluate, scf/src/molecular_orbitals.rs:37-43
+ *   chi_f(at) = sum_k c_k dx^l dy^m dz^n exp(-alpha_k |diff|^2), diff = position - at
+ *                                                 ContractedGaussian::evaluate, basis/src/contracted_gaussian.rs:320-331
+ * `coeff[N]` is one column of the coefficient matrix; functions with |coeff| <= min_coeff are dropped
+ * exactly as MolecularOrbitals::new does (molecular_orbitals.rs:70-79, MIN_COEFFICIENT_MAGNITUDE = 0.05,
+ * strict '>'); pass a negative min_coeff to keep every function.
+ * fock_orbital_eval: a batch of points `points[n][3]` (bohr) -> `values[n]` in FP64 -- the call
+ * pointcloud/src/main.rs:108 makes per Monte-Carlo sample.
+ * fock_orbital_voxelize: State::create_wave_texture_data (volumetric/src/main.rs:100-125): voxel
+ * i = x + n*y + n*n*z sits at ((x,y,z)/n - 0.5) * box_size; `grid[n^3]` receives psi `as f32`
+ * (the R32F texture image; the reference uses n = 200, box_size = 20.0). */
+int fock_orbital_eval(fock_ctx *ctx, const double *coeff, double min_coeff, const double *points, size_t n, double *values);
+int fock_orbital_voxelize(fock_ctx *ctx, const double *coeff, double min_coeff, int32_t n_voxels, double box_size, float *grid);
+/* Kernel time (ms, CUDA events) and the number of functions kept / exponent groups of the last fock_orbital_voxelize. */
+int fock_orbital_stats(fock_ctx *ctx, double *kernel_ms, int32_t *functions, int32_t *groups);
 
 /* Use a caller-provided cudaStream_t for all launches (NULL = the context's own stream). */
 int fock_set_stream(fock_ctx *ctx, void *cuda_stream);

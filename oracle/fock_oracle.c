@@ -623,3 +623,49 @@ void oracle_one_electron(const oracle_basis *bs, int n_nuclei, const double *nuc
         }
     }
 }
+
+/* ------------------------------------------------------------------ orbital evaluation (section 8 row f4) */
+
+/* ContractedGaussian::evaluate (basis/src/contracted_gaussian.rs:320-331): diff = position - at;
+ * fold over the primitives of  coefficient * dx^i * dy^j * dz^k * exp(-exponent * |diff|^2).
+ * nalgebra's norm_squared of a 3-vector is (x*x + y*y) + z*z. */
+static double basis_evaluate(const oracle_basis *bs, int f, const double at[3]) {
+    const double *pos = bs->center + 3 * f;
+    const double dx = pos[0] - at[0], dy = pos[1] - at[1], dz = pos[2] - at[2];
+    const double dist_sq = dx * dx + dy * dy + dz * dz;
+    const int32_t *l = bs->angular + 3 * f;
+    double acc = 0.0;
+    for (int k = bs->prim_offset[f]; k < bs->prim_offset[f + 1]; ++k)
+        acc = acc + bs->coefficient[k] * powi(dx, l[0]) * powi(dy, l[1]) * powi(dz, l[2]) * exp(-bs->exponent[k] * dist_sq);
+    return acc;
+}
+
+/* MolecularOrbital::evaluate (scf/src/molecular_orbitals.rs:37-43) over the functions
+ * MolecularOrbitals::new keeps (|coeff| > min_coeff, strict; :70-79). */
+static double orbital_evaluate(const oracle_basis *bs, const double *coeff, double min_coeff, const double at[3]) {
+    double sum = 0.0;
+    for (int f = 0; f < bs->n_basis; ++f)
+        if (fabs(coeff[f]) > min_coeff) sum = sum + coeff[f] * basis_evaluate(bs, f, at);
+    return sum;
+}
+
+void oracle_orbital_eval(const oracle_basis *bs, const double *coeff, double min_coeff, const double *points, int64_t n,
+                         double *values) {
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) values[i] = orbital_evaluate(bs, coeff, min_coeff, points + 3 * i);
+}
+
+/* State::create_wave_texture_data (volumetric/src/main.rs:100-125): voxel i -> x = i % n,
+ * y = (i / n) % n, z = i / n^2; at = (x as f64 / n as f64 - 0.5) * BOX_SIZE; stored `as f32`.
+ * Voxels [begin, end) only, so tests and the CPU baseline can take a bounded slab. */
+void oracle_voxelize(const oracle_basis *bs, const double *coeff, double min_coeff, int n_voxels, double box_size,
+                     int64_t begin, int64_t end, float *grid) {
+    const int64_t nv = n_voxels;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = begin; i < end; ++i) {
+        const double at[3] = {((double)(i % nv) / (double)nv - 0.5) * box_size,
+                              ((double)((i / nv) % nv) / (double)nv - 0.5) * box_size,
+                              ((double)(i / (nv * nv)) / (double)nv - 0.5) * box_size};
+        grid[i - begin] = (float)orbital_evaluate(bs, coeff, min_coeff, at);
+    }
+}

@@ -71,6 +71,10 @@ def lib():
         L.oracle_build_g.argtypes = [dp, C.c_int, dp, dp, C.c_int]
         L.oracle_one_electron.restype = None
         L.oracle_one_electron.argtypes = [bp, C.c_int, dp, dp, C.c_int, dp, dp, dp]
+        L.oracle_orbital_eval.argtypes = [bp, dp, C.c_double, dp, C.c_int64, dp]
+        L.oracle_orbital_eval.restype = None
+        L.oracle_voxelize.argtypes = [bp, dp, C.c_double, C.c_int, C.c_double, C.c_int64, C.c_int64, C.POINTER(C.c_float)]
+        L.oracle_voxelize.restype = None
         _lib = L
     return _lib
 
@@ -181,3 +185,24 @@ def one_electron(ob, nuc_pos, nuc_charge, flags=0):
     V = np.zeros((n, n), order="F")
     lib().oracle_one_electron(C.byref(ob.c), pos.shape[0], _dp(pos), _dp(chg), flags, _dp(S), _dp(T), _dp(V))
     return np.array(S), np.array(T), np.array(V)
+
+
+def orbital_eval(ob, coeff, points, min_coeff=0.05):
+    """MolecularOrbital::evaluate at a batch of points (FP64)."""
+    c = np.ascontiguousarray(coeff, dtype=np.float64)
+    assert c.shape == (ob.n,)
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros(pts.shape[0], dtype=np.float64)
+    lib().oracle_orbital_eval(C.byref(ob.c), _dp(c), float(min_coeff), _dp(pts), pts.shape[0], _dp(out))
+    return out
+
+
+def voxelize(ob, coeff, n_voxels=200, box_size=20.0, min_coeff=0.05, begin=0, end=None):
+    """State::create_wave_texture_data for voxels [begin, end) (f32, x fastest)."""
+    c = np.ascontiguousarray(coeff, dtype=np.float64)
+    assert c.shape == (ob.n,)
+    end = n_voxels ** 3 if end is None else end
+    out = np.zeros(max(end - begin, 0), dtype=np.float32)
+    lib().oracle_voxelize(C.byref(ob.c), _dp(c), float(min_coeff), int(n_voxels), float(box_size), int(begin), int(end),
+                          out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out

@@ -16,7 +16,7 @@ def water_dimer_xyz(shift_y=3.0):
 
 @functools.lru_cache(maxsize=None)
 def atoms_for(name, basis):
-    bs = BasisSet.named(basis)
+    bs = BasisSet.named(basis, general_contraction=basis.startswith("cc-"))
     if name == "water":
         return tuple(read_xyz_file(shipped_molecule("water"), bs))
     if name == "benzene":

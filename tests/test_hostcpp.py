@@ -42,3 +42,9 @@ def test_hostcpp_matches_oracle():
     np.testing.assert_allclose(eris, want, rtol=0, atol=1e-12)
     packed, _ = oracle.from_basis_packed(ob, oracle.FAITHFUL, fast=True)
     np.testing.assert_allclose(g, oracle.build_g(packed, 2, np.eye(2)), rtol=0, atol=1e-12)
+    psi = [float(x) for x in lines[2].split()]
+    c = np.array([0.55, 0.55])
+    want_psi = oracle.orbital_eval(ob, c, np.array([[0.0, 0.0, 0.6], [0.3, -0.2, 0.1]]))
+    np.testing.assert_allclose(psi[:2], want_psi, rtol=0, atol=1e-13)
+    grid = oracle.voxelize(ob, c, 2, 4.0)
+    np.testing.assert_allclose(psi[2:], [grid[0], grid[7]], rtol=1e-6, atol=0)

@@ -34,3 +34,21 @@ boys = np.array([[oracle.boys(float(x), n) for x in t] for n in range(11)])
 boys_exact = np.array([[oracle.boys_exact(float(x), n) for x in t] for n in range(11)])
 np.savez_compressed(os.path.join(OUT, "boys.npz"), t=t, faithful=boys, exact=boys_exact)
 print("wrote", sorted(os.listdir(OUT)))
+
+# Orbital evaluation (section 8 row f4): synthetic coefficient columns, random points, one small voxel grid.
+from test_orbital import CASES as ORB_CASES, coeff_for, points_for  # noqa: E402
+
+orb = {}
+pts = points_for(flat_for("water", "6-31G"), 300)
+orb["points"] = pts
+for mol, basis in ORB_CASES:
+    tag = f"{mol}_{basis}".replace("*", "s").replace("-", "")
+    fb = flat_for(mol, basis)
+    ob = oracle.OracleBasis.from_flat(fb)
+    c = coeff_for(fb.n_basis)
+    orb[f"coeff_{tag}"] = c
+    orb[f"values_{tag}"] = oracle.orbital_eval(ob, c, pts)
+    if tag == "water_631G":
+        orb["grid16_water_631G"] = oracle.voxelize(ob, c, 16, 20.0)
+np.savez_compressed(os.path.join(OUT, "orbital.npz"), **orb)
+print("wrote orbital.npz")
