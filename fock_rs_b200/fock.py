@@ -151,7 +151,7 @@ class FockBuilder:
         c = np.ascontiguousarray(coeff, dtype=np.float64)
         if c.shape != (self.n,):
             raise ValueError("coeff must have N entries")
-        out = np.empty(int(n_voxels) ** 3, dtype=np.float32)
+        out = np.empty(max(int(n_voxels), 0) ** 3, dtype=np.float32)  # a negative size is reported by the C ABI (FOCK_ERR_BAD_ARG)
         self._check(self._L.fock_orbital_voxelize(self._ctx, _dp(c), float(min_coeff), int(n_voxels), float(box_size),
                                                   out.ctypes.data_as(C.POINTER(C.c_float))))
         return out
