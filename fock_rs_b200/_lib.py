@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfock_b200.so")
+# FOCK_B200_LIB: measure an experimental build of the same ABI (tools/); the shipped library is the in-tree one
+LIB_PATH = os.environ.get("FOCK_B200_LIB") or os.path.join(_HERE, "libfock_b200.so")
 
 OK, ERR_BAD_ARG, ERR_BOYS_ORDER, ERR_CUDA, ERR_OOM, ERR_STATE, ERR_UNSUPPORTED = range(7)
 _NAMES = {1: "FOCK_ERR_BAD_ARG", 2: "FOCK_ERR_BOYS_ORDER", 3: "FOCK_ERR_CUDA", 4: "FOCK_ERR_OOM", 5: "FOCK_ERR_STATE", 6: "FOCK_ERR_UNSUPPORTED"}
