@@ -458,7 +458,7 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
         }
     }
     static const int kStreams = getenv("FOCK_STREAMS") ? std::max(1, std::min(kAuxStreams, atoi(getenv("FOCK_STREAMS")))) : kAuxStreams;
-    static const int kBlocksPerSm = getenv("FOCK_BLOCKS_PER_SM") ? atoi(getenv("FOCK_BLOCKS_PER_SM")) : 8;
+    static const int kBlocksPerSm = getenv("FOCK_BLOCKS_PER_SM") ? atoi(getenv("FOCK_BLOCKS_PER_SM")) : 16;
     cudaEventRecord(ev_fork, stream);
     for (int i = 0; i < kAuxStreams; ++i) cudaStreamWaitEvent(aux[i], ev_fork, 0);
     int slot = 0;
@@ -478,7 +478,7 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
         const long long mine = (pl.total_tiles - plan_rank + plan_world - 1) / plan_world;  // warp tiles of this rank
         if (mine <= 0) continue;
         // persistent blocks: enough to fill the machine, each strides over the warp tiles
-        dim3 grid((unsigned)std::min<long long>((mine + kClassWarps - 1) / kClassWarps, (long long)num_sms * kBlocksPerSm));
+        dim3 grid((unsigned)std::min<long long>((mine + kClassWarps - 1) / kClassWarps, (long long)num_sms * std::max(1, kBlocksPerSm * 128 / kClassThreads)));  // kBlocksPerSm counts 128-thread blocks
         int l = launch_class(pl.cb, pl.ck, cl, sink, mode, grid, aux[slot % kStreams]);
         if (l == 0) {
             // no register-resident kernel for this class pair (total angular momentum >= 6): one warp per

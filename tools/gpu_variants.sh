@@ -5,8 +5,11 @@ O=gpurun_out/variants.log
 : > $O
 for lib in default $(ls build/var/libfock_*.so 2>/dev/null); do
   if [ "$lib" = default ]; then unset FOCK_B200_LIB; else export FOCK_B200_LIB=$PWD/$lib; fi
-  for cfg in "alkane40 6-31G 0 1" "w16 6-31G 0 0" "w32 6-31G** 0 1" "w32 cc-pVDZ 0 1"; do
-    TAG=$(basename $lib) timeout 120 python tools/time_config.py $cfg 2>&1 | head -1 >> $O
+  for cfg in "alkane40 6-31G 0 1" "w16 6-31G 0 0" "benzene 6-31G 0 0"; do
+    for rep in 1 2; do TAG=$(basename $lib) timeout 120 python tools/time_config.py $cfg 2>&1 | head -1 >> $O; done
   done
 done
 cat $O
+if [ -n "$CHECK_LIB" ]; then
+  FOCK_B200_LIB=$PWD/$CHECK_LIB timeout 600 python -m pytest tests/test_golden.py tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
+fi
