@@ -254,7 +254,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "shell_quartets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 METRIC = "ERI+Fock-build unique shell quartets/s per SCF iteration (ms_per_step = ERI+Fock-build time per SCF iteration)"
@@ -329,13 +329,14 @@ def run_ours(args):
         if world > 1:
             parallel.allreduce_device(G)
 
+    staged = parallel.HostStagedG(b, stream) if world > 1 else None  # N > 1: partials are summed on the device, one PCIe round trip
+
     def step_host():
         if not direct:
             b.eri_build()
-        g = b.build_g(Dh)
-        if world > 1:
-            g = parallel.allreduce_host_matrix(g)
-        return g
+        if staged is not None:
+            return staged(Dh)
+        return b.build_g(Dh)
 
     def timed(fn, steps):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -384,7 +385,8 @@ def run_ours(args):
             if (wl, stor) != (args.workload, args.storage):
                 others.append(quick_config(wl, stor, "ref", rank, world, local, incore_shard=1 if args.incore_shard == "build" else 0))
     if rank == 0:
-        eri_tf = st["model_flops"] / (tm["class_kernels_ms"] * 1e-3) * 1e-12 if tm["class_kernels_ms"] > 0 else 0.0
+        # model flops are counted over all ranks; the roofline is per GPU (tiles are dealt evenly), against one GPU's peak
+        eri_tf = st["model_flops"] / world / (tm["class_kernels_ms"] * 1e-3) * 1e-12 if tm["class_kernels_ms"] > 0 else 0.0
         streamed = nelem / (world if (world > 1 and args.incore_shard == "digest") else 1)
         g_gbs = 8.0 * streamed / max(tm["g_device_ms"], 1e-9) * 1e-6 if storage == _lib.STORAGE_INCORE else 0.0
         parts = {"diag_ms": tm["diag_ms"] if not direct else 0.0, "eri_ms": tm["eri_ms"] if not direct else 0.0,
@@ -397,7 +399,7 @@ def run_ours(args):
         roof_eri = {"bound": "fp64", "achieved": eri_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": eri_tf / fp64_peak if fp64_peak else None,
                     "traffic": ncu_traffic(args.workload, storage == _lib.STORAGE_DIRECT),
                     "kernel": "eri_class_kernel<*> (all class / slice launches of one build, CUDA events around them)",
-                    "note": "model flops of the quartets evaluated (SURVEY.md 8d formula) / time between the events bracketing the class launches; peak = DFMA-chain probe measured in this run"}
+                    "note": "model flops of the quartets evaluated (SURVEY.md 8d formula; per GPU = total / n_gpus) / time between the events bracketing the class launches; peak = DFMA-chain probe measured in this run (one GPU)"}
         # DRAM bytes of one symv launch from the committed ncu --set full capture (profiles/r01_*_ncu_full_w16_refcut.md)
         symv_traffic = 1.894e9 if (args.workload == "w16" and world == 1 and storage == _lib.STORAGE_INCORE) else None
         roof_g = {"bound": "hbm", "achieved": g_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": g_gbs / hbm_peak, "traffic": symv_traffic,
@@ -406,7 +408,7 @@ def run_ours(args):
             "metric": METRIC, "value": nq / (ms_step * 1e-3), "unit": "shell_quartets/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, flat),
-            "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "shell_quartets/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 8 * n * n, "d2h_bytes_per_step": 8 * n * n},
+            "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "shell_quartets/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 8 * n * n * world, "d2h_bytes_per_step": 8 * n * n * world},
             "gpu_launches": int((st["launches_g"] if direct else st["launches_build"] + st["launches_g"]) * args.steps),
             "clocks": clocks.summary(),
             "roofline": roof_g if (dominant == "g_ms" and storage == _lib.STORAGE_INCORE) else roof_eri,
@@ -421,7 +423,7 @@ def run_ours(args):
             line["orbital_voxelizer"] = voxel_config(local, with_cpu=not args.no_cpu_baseline)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = {k: v for k, v in cpu_baseline(args.workload, args.screen == "ref", args.cpu_budget, nq).items() if k not in ("checksum",)}
-        print(json.dumps(line))
+        emit(line)
     b.close()
     if dist is not None:
         dist.barrier()
@@ -528,10 +530,28 @@ def quick_config(workload, storage, screen, rank, world, local, steps=5, incore_
             "shell_quartets_per_s": nq / (ms * 1e-3), "shell_quartets_unique": nq, "shell_quartets_evaluated": stt["shell_quartets_evaluated"],
             "class_kernels_ms": tm["class_kernels_ms"], "g_device_ms": tm["g_device_ms"],
             "digest_hbm_gbs": (8.0 * b_len / (world if incore_shard == 0 else 1) / (tm["g_device_ms"] * 1e-3) * 1e-9) if storage == "incore" else None,
-            "class_kernels_model_tflops": stt["model_flops"] / (tm["class_kernels_ms"] * 1e-3) * 1e-12 if tm["class_kernels_ms"] > 0 else None}
+            "class_kernels_model_tflops": stt["model_flops"] / world / (tm["class_kernels_ms"] * 1e-3) * 1e-12 if tm["class_kernels_ms"] > 0 else None}  # per GPU
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything libraries print while the bench runs
+    (NCCL's version banner, for one) has been routed to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)

@@ -258,6 +258,7 @@ class FockEngine:
     def __init__(self, mode=_lib.MODE_FAITHFUL, screen=_lib.SCREEN_REFERENCE, tau=1e-6, storage=_lib.STORAGE_INCORE, device=-1, distributed=None):
         self.kw = dict(mode=mode, screen=screen, tau=tau, storage=storage, device=device)
         self.builder: Optional[FockBuilder] = None
+        self._staged = None
         self.rank, self.world = 0, 1
         if distributed is None:
             try:
@@ -287,9 +288,16 @@ class FockEngine:
         b.eri_build()
 
     def build_g(self, D):
-        G = self.builder.build_g(D)
         if self.distributed and self.world > 1:
+            import torch.distributed as dist
+
+            if dist.get_backend() == "nccl":  # one PCIe round trip, partials summed on the device
+                from .parallel import HostStagedG
+
+                if self._staged is None or self._staged.b is not self.builder:
+                    self._staged = HostStagedG(self.builder)
+                return self._staged(D)
             from .parallel import allreduce_host_matrix
 
-            G = allreduce_host_matrix(G)
-        return G
+            return allreduce_host_matrix(self.builder.build_g(D))
+        return self.builder.build_g(D)

@@ -64,3 +64,39 @@ def allreduce_device(g_tensor):
 
     dist.all_reduce(g_tensor, op=dist.ReduceOp.SUM)
     return g_tensor
+
+
+class HostStagedG:
+    """G build for HOST matrices on `world` ranks with ONE PCIe round trip per call: D goes pinned host -> device,
+    `fock_build_g_device` produces this rank's partial G, the partials are summed on the device (one NCCL
+    all-reduce of N*N doubles) and only the sum returns to the host.  (`fock_build_g` + `allreduce_host_matrix`
+    would move G down, up again for NCCL and down once more.)  D must be symmetric, as the reference's density
+    is; G is symmetric, so row- and column-major images coincide."""
+
+    def __init__(self, builder, stream=None):
+        import torch
+
+        self.b = builder
+        n = builder.n
+        self.stream = stream if stream is not None else torch.cuda.Stream()  # never the legacy default stream
+        self.Dp = torch.empty((n, n), dtype=torch.float64).pin_memory()
+        self.Gp = torch.empty((n, n), dtype=torch.float64).pin_memory()
+        with torch.cuda.stream(self.stream):
+            self.D = torch.empty((n, n), dtype=torch.float64, device="cuda")
+            self.G = torch.empty((n, n), dtype=torch.float64, device="cuda")
+        self.stream.synchronize()
+
+    def __call__(self, D_host) -> np.ndarray:
+        import torch
+        import torch.distributed as dist
+
+        self.Dp.copy_(torch.from_numpy(np.ascontiguousarray(D_host, dtype=np.float64)))
+        with torch.cuda.stream(self.stream):
+            self.b.set_stream(self.stream.cuda_stream)
+            self.D.copy_(self.Dp, non_blocking=True)
+            self.b.build_g_device(self.D.data_ptr(), self.G.data_ptr())
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.all_reduce(self.G, op=dist.ReduceOp.SUM)
+            self.Gp.copy_(self.G, non_blocking=True)
+        self.stream.synchronize()
+        return self.Gp.numpy().copy()
