@@ -229,3 +229,24 @@ def test_molecular_orbitals_mirror_after_scf():
         assert np.max(np.abs(mos[n].evaluate_many(pts) - want)) <= 1e-13
         assert abs(mos[n].evaluate(pts[0]) - want[0]) <= 1e-13
         _assert_f32_grid_close(mos[n].voxelize(24, 12.0), oracle.voxelize(ob, col, 24, 12.0))
+
+
+@pytest.mark.gpu
+def test_cuda_orbital_deep_contraction_path():
+    """Contractions longer than the kernel's 8-entry exponential cache (the 9-primitive s functions of the cc-pVDZ-shaped
+    set) take the per-function branch, which recomputes exp() per function exactly as the reference does."""
+    from fock_rs_b200.fock import FockBuilder
+
+    fb = flat_for("water", "cc-pVDZ")
+    assert int(np.max(np.diff(np.asarray(fb.prim_offset)))) == 9
+    ob = oracle.OracleBasis.from_flat(fb)
+    c = coeff_for(fb.n_basis, seed=12)
+    c[5] = 0.8  # make sure both 9-primitive functions are kept
+    c[6] = -0.6
+    pts = points_for(fb, 2000)
+    with FockBuilder(fb) as b:
+        got = b.orbital_eval(c, pts)
+        grid = b.orbital_voxelize(c, 32, 8.0)
+    want = oracle.orbital_eval(ob, c, pts)
+    assert np.max(np.abs(got - want)) <= 1e-12 * max(1.0, float(np.max(np.abs(want))))
+    _assert_f32_grid_close(grid, oracle.voxelize(ob, c, 32, 8.0))
