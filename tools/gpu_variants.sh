@@ -1,5 +1,7 @@
 #!/bin/bash
-# A/B timing of experimental library builds (build/var/libfock_*.so) against the in-tree one.
+# A/B timing of experimental library builds (build/var/libfock_*.so, made by tools/build_variants.sh) against the in-tree one;
+# CHECK_LIB=build/var/libfock_<name>.so additionally runs the golden + parity GPU tests against that build.
+# usage (on the GPU box):  gpurun -- 'CHECK_LIB=build/var/libfock_nq.so bash tools/gpu_variants.sh'
 mkdir -p gpurun_out
 O=gpurun_out/variants.log
 : > $O
