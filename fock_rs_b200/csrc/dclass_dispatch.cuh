@@ -45,8 +45,10 @@ inline int launch_ket_range(const ClassLaunch &cl, const Sink &sink, dim3 grid, 
 }
 
 // Class pairs with total angular momentum 6..8, integral-direct sink only (dclass_hi_*.cu): with ONE ket
-// component per slice the compiler keeps only the sub-box of the R table that component reaches, so even
-// (dd|dd) stays in registers.  In-core builds of these classes use the warp-per-quartet fallback.
+// component per slice the compiler keeps only the sub-box of the R table that component reaches.  That fits
+// the register file up to (dd|pp)/(dd|ds); the (dp|dp), (dd|dp) and (dd|dd) slices run at 255 registers with
+// 3.5-8 KB of the table per thread in local memory (profiles/r01_v22_ptxas_class_kernels.md).  In-core builds
+// of these classes use the warp-per-quartet fallback.
 int launch_hi_dpdp(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
 int launch_hi_ddpp(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
 int launch_hi_ddds(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
