@@ -1,14 +1,44 @@
-import sys, time, os; sys.path.insert(0,'.'); sys.path.insert(0,'tests')
-import numpy as np
-from fock_rs_b200.fock import FockBuilder
-from fock_rs_b200 import _lib
-from helpers import flat_for, random_symmetric_density
-mol,basis,screen,storage = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
-fb=flat_for(mol,basis)
-D=random_symmetric_density(fb.n_basis)
-with FockBuilder(fb,screen=screen,storage=storage,keep_eri=False) as b:
-    b.eri_build(); G=b.build_g(D)
-    t0=time.time(); b.eri_build(); t1=time.time(); G=b.build_g(D); t2=time.time()
-    tm=b.timings(); st=b.stats()
-    print(os.environ.get('TAG',''), mol, 'screen',screen,'storage',storage,'build %.2f ms g %.2f ms | class %.3f g_dev %.3f sort %.2f plan %.2f tiles %d TF %.2f'%(1e3*(t1-t0),1e3*(t2-t1),tm['class_kernels_ms'],tm['g_device_ms'],tm['host_sort_ms'],tm['host_plan_ms'],st['warp_tiles'], st['model_flops']/(tm['class_kernels_ms']*1e-3)*1e-12), flush=True)
-    print({k: st[k] for k in ("shells", "shell_quartets_unique", "shell_quartets_evaluated", "general_shell_quartets_evaluated", "prim_quartets_evaluated", "launches_build", "launches_g")})
+#!/usr/bin/env python3
+"""One build + one G build of a named molecule/basis on cuda:0, timed after a warm-up pass; prints the library's own
+timings and counters.  The quick A/B probe used by tools/gpu_variants.sh (TAG labels the line, FOCK_B200_LIB picks an
+experimental build).
+
+usage: tools/time_config.py <molecule> <basis> <screen: 0 ref | 1 off> <storage: 0 in-core | 1 direct>
+  e.g. tools/time_config.py alkane40 6-31G 0 1      tools/time_config.py w32 'cc-pVDZ' 0 1
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from fock_rs_b200.fock import FockBuilder  # noqa: E402
+from helpers import flat_for, random_symmetric_density  # noqa: E402
+
+
+def main():
+    mol, basis, screen, storage = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+    fb = flat_for(mol, basis)
+    D = random_symmetric_density(fb.n_basis)
+    with FockBuilder(fb, screen=screen, storage=storage, keep_eri=False) as b:
+        b.eri_build()
+        b.build_g(D)  # warm-up
+        t0 = time.time()
+        b.eri_build()
+        t1 = time.time()
+        b.build_g(D)
+        t2 = time.time()
+        tm, st = b.timings(), b.stats()
+    tflops = st["model_flops"] / (tm["class_kernels_ms"] * 1e-3) * 1e-12 if tm["class_kernels_ms"] > 0 else 0.0
+    print(os.environ.get("TAG", ""), mol, "screen", screen, "storage", storage,
+          "build %.2f ms g %.2f ms | class %.3f g_dev %.3f sort %.2f plan %.2f tiles %d TF %.2f"
+          % (1e3 * (t1 - t0), 1e3 * (t2 - t1), tm["class_kernels_ms"], tm["g_device_ms"], tm["host_sort_ms"], tm["host_plan_ms"],
+             st["warp_tiles"], tflops), flush=True)
+    print({k: st[k] for k in ("shells", "shell_quartets_unique", "shell_quartets_evaluated", "general_shell_quartets_evaluated",
+                              "prim_quartets_evaluated", "launches_build", "launches_g")})
+
+
+if __name__ == "__main__":
+    main()
