@@ -27,7 +27,9 @@ EXPORTS = [
     "fock_supermatrix_device", "fock_set_digest_range", "fock_timings", "fock_stats", "fock_last_error", "fock_destroy",
     "fock_abi_version", "fock_measure_fp64_peak", "fock_boys_batch",
     "fock_orbital_eval", "fock_orbital_voxelize", "fock_orbital_stats",
+    "fock_diagonal_export", "fock_comm_unique_id", "fock_comm_init", "fock_comm_destroy", "fock_comm_attached", "fock_comm_last_error",
 ]
+COMM_ID_BYTES = 128
 
 
 class FockError(RuntimeError):
@@ -59,6 +61,7 @@ class COpts(C.Structure):
         ("keep_eri", C.c_int32),
         ("kernel", C.c_int32),
         ("incore_shard", C.c_int32),
+        ("deterministic", C.c_int32),
     ]
 
 
@@ -104,5 +107,13 @@ def load():
     L.fock_orbital_eval.argtypes = [vp, dp, C.c_double, dp, C.c_size_t, dp]
     L.fock_orbital_voxelize.argtypes = [vp, dp, C.c_double, C.c_int32, C.c_double, C.POINTER(C.c_float)]
     L.fock_orbital_stats.argtypes = [vp, dp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.fock_diagonal_export.argtypes = [vp, dp, C.c_size_t]
+    L.fock_comm_unique_id.argtypes = [C.c_char_p]
+    L.fock_comm_init.argtypes = [vp, C.c_char_p]
+    L.fock_comm_destroy.argtypes = [vp]
+    L.fock_comm_attached.argtypes = [vp]
+    L.fock_comm_last_error.restype = C.c_char_p
+    if L.fock_abi_version() != 4:
+        raise ImportError(f"{LIB_PATH} implements ABI version {L.fock_abi_version()}, this package binds version 4: rebuild it")
     _lib = L
     return L

@@ -19,7 +19,7 @@ namespace {
 template <int LA, int LB, int LC, int LD, int KC0, int KCN, class Sink>
 void launch_mode(const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, cudaStream_t st) {
     constexpr int NAB = ncart_c(LA) * ncart_c(LB);
-    const size_t smem = boys_smem_doubles(LA + LB + LC + LD, cl.boys_ni) * sizeof(double) + near_queue_smem_bytes(LA, LB, LC, LD, NAB * KCN);
+    const size_t smem = boys_smem_bytes(LA + LB + LC + LD, cl.boys_ni) + near_queue_smem_bytes(LA, LB, LC, LD, NAB * KCN);
     if (mode & FOCK_MODE_FIX_R_BIT)
         eri_class_kernel<LA, LB, LC, LD, 1, 0, NAB, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
     else
@@ -50,7 +50,7 @@ int launch_class(int cb, int ck, const ClassLaunch &cl, const Sink &sink, int mo
 
 template <int LA, int LB, int KC0, int KCN>
 void launch_diag_mode(const DiagLaunch &dl, const DiagSink &sink, int mode, dim3 grid, cudaStream_t st) {
-    const size_t smem = boys_smem_doubles(2 * (LA + LB), dl.boys_ni) * sizeof(double);
+    const size_t smem = boys_smem_bytes(2 * (LA + LB), dl.boys_ni);
     if (mode & FOCK_MODE_FIX_R_BIT)
         eri_diag_kernel<LA, LB, 1, KC0, KCN><<<grid, kClassThreads, smem, st>>>(dl, sink);
     else
@@ -59,13 +59,16 @@ void launch_diag_mode(const DiagLaunch &dl, const DiagSink &sink, int mode, dim3
 
 // sorted tables from the natural-order master: position i of a sublist takes natural pair perm[i].
 // One launch for all sublists; block = one pair.
-__global__ void permute_pairs_kernel(PermuteTable tab, const double *__restrict__ bra_nat, const int *__restrict__ meta_nat,
+__global__ void permute_pairs_kernel(const PermuteDesc *__restrict__ descs, int count, const double *__restrict__ bra_nat, const int *__restrict__ meta_nat,
                                      const int *__restrict__ perm, double *__restrict__ bra, double *__restrict__ ket,
                                      int *__restrict__ meta) {
     const int g = blockIdx.x;
-    int s = 0;
-    while (s + 1 < tab.count && g >= tab.d[s + 1].first) ++s;
-    const PermuteDesc d = tab.d[s];
+    int s = 0, hi = count - 1;  // largest s with descs[s].first <= g
+    while (s < hi) {
+        const int mid = (s + hi + 1) >> 1;
+        if (descs[mid].first <= g) s = mid; else hi = mid - 1;
+    }
+    const PermuteDesc d = descs[s];
     const int i = g - d.first;
     if (i >= d.n) return;
     const int src = perm[d.meta_off / 2 + i];
@@ -98,13 +101,29 @@ __global__ void class_pairmax_kernel(const int *__restrict__ meta_nat, const int
     maxdiag[first + i] = (unsigned long long)__double_as_longlong(m);
 }
 
+// (job, first row) of every warp tile of a class launch: what the kernel would otherwise search for per tile
+// (two dependent ballot rounds over the job table, three over the row prefixes); one thread per tile, once per plan.
+__global__ void tile_table_kernel(const ClassJob *__restrict__ jobs, int njobs, long long total_tiles, int2 *__restrict__ out) {
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total_tiles; t += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = njobs - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
+        }
+        const long long *prefix = jobs[lo].row_prefix;
+        const long long q0 = (t - jobs[lo].tile_begin) * (32 / jobs[lo].ksplit);
+        int a = 0, b = jobs[lo].nb - 1;
+        while (a < b) {  // largest row with prefix[row] <= q0 (skips empty rows, like warp_search)
+            const int mid = (a + b + 1) >> 1;
+            if (prefix[mid] <= q0) a = mid; else b = mid - 1;
+        }
+        out[t] = make_int2(lo, a);
+    }
+}
+
 }  // namespace
 
 int ClassEngine::upload_master(std::string &err) {
-    if ((int)sd->sublists.size() > kMaxSublists) {
-        err = "more (class, primitive-count) sublists than the class engine supports";
-        return 1;
-    }
     std::vector<double> bra, ket;
     std::vector<int> meta;
     build_pair_tables(*sd, bra, ket, meta);
@@ -155,7 +174,7 @@ int ClassEngine::upload_master(std::string &err) {
     {
         const int npairs = (int)(meta.size() / 2), nseg = (int)sd->sublists.size();
         std::vector<int> iota(npairs), seg(2 * nseg);
-        permute_tab = PermuteTable{};
+        std::vector<PermuteDesc> descs;
         int first = 0;
         for (int si = 0; si < nseg; ++si) {
             const Sublist &s = sd->sublists[si];
@@ -164,11 +183,17 @@ int ClassEngine::upload_master(std::string &err) {
             seg[si] = base;
             seg[nseg + si] = base + n;
             if (n > 0) {
-                permute_tab.d[permute_tab.count++] = PermuteDesc{s.bra_off, s.ket_off, s.meta_off, first, n, s.K, s.nf, s.npad};
+                descs.push_back(PermuteDesc{s.bra_off, s.ket_off, s.meta_off, first, n, s.K, s.nf, s.npad});
                 first += n;
             }
         }
         permute_blocks = first;
+        permute_count = (int)descs.size();
+        if ((e = cudaMalloc((void **)&d_permute_desc, (descs.size() + 1) * sizeof(PermuteDesc))) != cudaSuccess) {
+            err = std::string("permutation table: ") + cudaGetErrorString(e);
+            return 1;
+        }
+        cudaMemcpy(d_permute_desc, descs.data(), descs.size() * sizeof(PermuteDesc), cudaMemcpyHostToDevice);
         cudaMemcpy(d_iota, iota.data(), iota.size() * sizeof(int), cudaMemcpyHostToDevice);
         cudaMemcpy(d_seg, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice);
         sort_temp_bytes = 0;
@@ -178,6 +203,24 @@ int ClassEngine::upload_master(std::string &err) {
             err = std::string("sort scratch: ") + cudaGetErrorString(e);
             return 1;
         }
+    }
+    // the Boys tables in the staged layout of every total angular momentum, in global memory
+    if ((e = cudaMalloc((void **)&d_boys_stage, (boys_stage_off(9, boys_ni) + 8) * sizeof(double))) != cudaSuccess) {
+        err = std::string("Boys stage image: ") + cudaGetErrorString(e);
+        return 1;
+    }
+    boys_stage_kernel<0><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
+    boys_stage_kernel<1><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
+    boys_stage_kernel<2><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
+    boys_stage_kernel<3><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
+    boys_stage_kernel<4><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
+    boys_stage_kernel<5><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
+    boys_stage_kernel<6><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
+    boys_stage_kernel<7><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
+    boys_stage_kernel<8><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) {
+        err = std::string("Boys stage image: ") + cudaGetErrorString(e);
+        return 1;
     }
     plan_valid = false;
     return 0;
@@ -193,7 +236,7 @@ int ClassEngine::run_diagonal(double *d_diag, std::string &err) {
         const Sublist &s = sd->sublists[si];
         const int n = (int)s.pair_ids.size();
         if (!n) continue;
-        DiagLaunch dl{d_bra_nat + s.bra_off, d_meta_nat + s.meta_off, dev->d_shell_bf, boys_poly, boys_ni, s.K, n, (int)(s.meta_off / 2)};
+        DiagLaunch dl{d_bra_nat + s.bra_off, d_meta_nat + s.meta_off, dev->d_shell_bf, boys_poly, boys_ni, s.K, n, (int)(s.meta_off / 2), d_boys_stage};
         dim3 grid((unsigned)std::min((n + kClassWarps - 1) / kClassWarps, num_sms * 4));
         if (s.cls == 0) {
             launch_diag_mode<0, 0, 0, 1>(dl, sink, mode, grid, stream);
@@ -233,7 +276,7 @@ int ClassEngine::finish_diagonal(const double *d_diag, std::string &err) {
     cub::DeviceSegmentedSort::SortPairsDescending(d_sort_temp, sort_temp_bytes, d_maxdiag, d_keys_sorted, d_iota, d_perm, (int)npairs,
                                                   nseg, d_seg, d_seg + nseg, stream);
     if (permute_blocks > 0)
-        permute_pairs_kernel<<<permute_blocks, 64, 0, stream>>>(permute_tab, d_bra_nat, d_meta_nat, d_perm, dev->d_bra, dev->d_ket,
+        permute_pairs_kernel<<<permute_blocks, 64, 0, stream>>>(d_permute_desc, permute_count, d_bra_nat, d_meta_nat, d_perm, dev->d_bra, dev->d_ket,
                                                                dev->d_meta);
     launches += 2;
     cudaMemcpyAsync(h_keys_sorted, d_keys_sorted, npairs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
@@ -393,10 +436,6 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
             }
             pl.njobs = (int)jobs.size() - pl.job_begin;
             pl.total_tiles = tiles_launch;
-            if (pl.njobs > kMaxJobs) {
-                err = "too many sublist pairs in one class launch";
-                return 1;
-            }
             if (pl.njobs > 0) plan.push_back(pl);
         }
     cudaError_t e;
@@ -432,6 +471,30 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
     std::copy(jobs.begin(), jobs.end(), h_jobs);
     cudaMemcpyAsync(d_table, h_table, table.size() * sizeof(long long), cudaMemcpyHostToDevice, stream);
     cudaMemcpyAsync(d_jobs, h_jobs, jobs.size() * sizeof(ClassJob), cudaMemcpyHostToDevice, stream);
+    // per-tile descriptors of every launch (one pass on the device; the plan is reused by every G build of a geometry)
+    {
+        long long all_tiles = 0;
+        for (ClassPlanLaunch &pl : plan) {
+            pl.tile_base = all_tiles;
+            all_tiles += pl.total_tiles;
+        }
+        if ((size_t)all_tiles + 1 > tile_tab_cap) {
+            if (d_tile_tab) cudaFree(d_tile_tab);
+    if (d_permute_desc) cudaFree(d_permute_desc);
+            d_tile_tab = nullptr;
+            tile_tab_cap = (size_t)all_tiles + (size_t)all_tiles / 8 + 1024;
+            if ((e = cudaMalloc((void **)&d_tile_tab, tile_tab_cap * sizeof(int2))) != cudaSuccess) {
+                err = std::string("tile descriptor table: ") + cudaGetErrorString(e);
+                tile_tab_cap = 0;
+                return 1;
+            }
+        }
+        for (const ClassPlanLaunch &pl : plan) {
+            if (pl.total_tiles <= 0) continue;
+            const unsigned blocks = (unsigned)std::min<long long>((pl.total_tiles + 255) / 256, (long long)num_sms * 16);
+            tile_table_kernel<<<blocks, 256, 0, stream>>>(d_jobs + pl.job_begin, pl.njobs, pl.total_tiles, d_tile_tab + pl.tile_base);
+        }
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         err = std::string("plan upload: ") + cudaGetErrorString(e);
@@ -473,6 +536,8 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
         cl.fix_r = (mode & FOCK_MODE_FIX_R_BIT) ? 1 : 0;
         cl.boys_poly = boys_poly;
         cl.boys_ni = boys_ni;
+        cl.boys_stage = d_boys_stage;
+        cl.tile_tab = d_tile_tab + pl.tile_base;
         cl.rank = plan_rank;
         cl.world = plan_world;
         const long long mine = (pl.total_tiles - plan_rank + plan_world - 1) / plan_world;  // warp tiles of this rank
@@ -512,6 +577,9 @@ template int ClassEngine::run_plan<BlockDirectSink>(const BlockDirectSink &, std
 
 ClassEngine::~ClassEngine() {
     if (d_table) cudaFree(d_table);
+    if (d_boys_stage) cudaFree(d_boys_stage);
+    if (d_tile_tab) cudaFree(d_tile_tab);
+    if (d_permute_desc) cudaFree(d_permute_desc);
     if (d_shell_scale) cudaFree(d_shell_scale);
     if (d_jobs) cudaFree(d_jobs);
     if (d_bra_nat) cudaFree(d_bra_nat);

@@ -41,16 +41,14 @@ struct ClassPlanLaunch {
     int cb = 0, ck = 0;       // pair classes 0 ss, 1 ps, 2 pp, 3 ds, 4 dp, 5 dd
     int job_begin = 0, njobs = 0;
     long long total_tiles = 0;
+    long long tile_base = 0;  // first entry of this launch in the engine's tile table
 };
 
-constexpr int kMaxSublists = 48;
+// one entry per non-empty sublist (class x primitive-pair count); the table lives in device memory, so the number of
+// distinct contraction depths of a basis is not limited
 struct PermuteDesc {
     size_t bra_off, ket_off, meta_off;
     int first, n, K, nf, npad;
-};
-struct PermuteTable {
-    PermuteDesc d[kMaxSublists];
-    int count;
 };
 
 struct ClassEngine {
@@ -58,6 +56,7 @@ struct ClassEngine {
     PairTablesDev *dev = nullptr;
     const double *boys_poly = nullptr;  // device, per-interval polynomial table of the active mode
     int boys_ni = 200;
+    double *d_boys_stage = nullptr;     // the same tables in the class kernels' staged layout, every L (eri_class.cuh: boys_stage_off)
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     int mode = 0;
@@ -80,11 +79,14 @@ struct ClassEngine {
     int *d_iota = nullptr, *d_seg = nullptr;
     void *d_sort_temp = nullptr;
     size_t sort_temp_bytes = 0;
-    PermuteTable permute_tab{};
+    PermuteDesc *d_permute_desc = nullptr;
+    int permute_count = 0;
     int permute_blocks = 0;
     double host_ms[4] = {0, 0, 0, 0};  // sort, plan
     ClassJob *d_jobs = nullptr;
     size_t jobs_cap = 0;
+    int2 *d_tile_tab = nullptr;  // (job, first row) per warp tile of every launch of the plan
+    size_t tile_tab_cap = 0;
     std::vector<ClassPlanLaunch> plan;
     ClassStats plan_stats;
     bool plan_valid = false;

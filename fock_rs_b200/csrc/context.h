@@ -11,7 +11,7 @@
 #include "eri_generic.cuh"
 #include "shells.h"
 
-enum { EV_A = 0, EV_B, EV_C, EV_D, EV_E, EV_F, EV_COUNT };
+enum { EV_A = 0, EV_B, EV_C, EV_D, EV_E, EV_F, EV_ORB0, EV_ORB1, EV_COUNT };  // EV_ORB*: the orbital path's own pair (fock_timings reads EV_E/EV_F as the last G build)
 
 struct fock_ctx {
     fock_opts opts{};
@@ -52,6 +52,10 @@ struct fock_ctx {
     int orbital_functions = 0, orbital_groups = 0;
     bool built = false;
     int device = 0;
+    void *comm = nullptr;      // ncclComm_t when fock_comm_init attached one (fock_comm.cu)
+    double det_scale = 0.0;    // deterministic mode: fixed-point scale of the last direct G build (a power of two)
+    double det_bound_jk = 0.0; // deterministic mode: bound of |A| per unit of max|D|, from the diagonal (fock_eri_build)
+    double *d_det = nullptr;   // deterministic mode: [2] device scalars (max |D| as bits, scratch)
     std::string err;
 
     fock::BasisDev basis_dev() const {
@@ -59,6 +63,10 @@ struct fock_ctx {
     }
     fock::BoysTables boys() const { return fock::BoysTables{d_boys_lut, d_boys_tab}; }
 };
+
+// fock_comm.cu: in-place sum of `buf` over the attached communicator's ranks on `st` (no-op without one);
+// `as_int64`: the buffer holds 64-bit fixed-point integers (deterministic mode)
+int fock_comm_allreduce(fock_ctx *ctx, void *buf, size_t n, bool as_int64, cudaStream_t st);
 
 #define FOCK_CUDA_TRY(ctx, expr)                                                                         \
     do {                                                                                                 \

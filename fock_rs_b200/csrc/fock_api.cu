@@ -100,6 +100,7 @@ void fock_default_opts(fock_opts *o) {
     o->keep_eri = 1;
     o->kernel = 0;
     o->incore_shard = 0;
+    o->deterministic = 0;
 }
 
 size_t fock_packed_len(int32_t n) {
@@ -126,6 +127,10 @@ int fock_create(const fock_basis *b, const fock_opts *opts_in, fock_ctx **out) {
         o.storage < 0 || o.storage > 1) {
         g_create_error = "bad options";
         return FOCK_ERR_BAD_ARG;
+    }
+    if (o.deterministic && o.storage != FOCK_STORAGE_DIRECT) {
+        g_create_error = "the deterministic (fixed-point) accumulation exists for integral-direct storage only";
+        return FOCK_ERR_UNSUPPORTED;
     }
     const int n = b->n_basis;
     if (n > 65535) {
@@ -272,6 +277,7 @@ int fock_create(const fock_basis *b, const fock_opts *opts_in, fock_ctx **out) {
             const int64_t sp = ctx->stats[2];
             ctx->stats[3] = sp * (sp + 1) / 2;
         }
+        ctx->stats[12] = ctx->shells.n_partial_shells;
         return FOCK_OK;
     };
     const int status = body();
@@ -285,6 +291,8 @@ void fock_destroy(fock_ctx *c) {
     fock_ctx_ext *ctx = static_cast<fock_ctx_ext *>(c);
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    fock_comm_destroy(ctx);
+    if (ctx->d_det) cudaFree(ctx->d_det);
     void *ptrs[] = {ctx->d_center, ctx->d_angular, ctx->d_primoff, ctx->d_exp,  ctx->d_coef, ctx->d_boys_lut,
                     ctx->d_boys_tab, ctx->d_diag,   ctx->d_V,       ctx->d_P,    ctx->d_dvec, ctx->d_yvec,
                     ctx->d_D,      ctx->d_G,       ctx->d_Ds,      ctx->d_A,    ctx->pairs.d_bra, ctx->pairs.d_ket, ctx->pairs.d_meta,
@@ -478,6 +486,26 @@ int fock_eri_build(fock_ctx *ctx) {
     } else {
         FOCK_TRY(diagonal_finish(ctx, &launches));
         FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+        if (ctx->opts.deterministic) {
+            // bound of every |A| element per unit of max|D| from Schwarz, |(xy|zw)| <= sqrt(d_xy d_zw):
+            //   Coulomb  <= 2 max sqrt(d) * sum_pairs sqrt(d),  exchange (4 forms) <= 2 (max_x sum_y sqrt(d_xy))^2
+            std::vector<double> hd(ctx->npair);
+            FOCK_CUDA_TRY(ctx, cudaMemcpy(hd.data(), ctx->d_diag, ctx->npair * sizeof(double), cudaMemcpyDeviceToHost));
+            std::vector<double> rowsum(ctx->N, 0.0);
+            double t1 = 0.0, dm = 0.0;
+            size_t xy = 0;
+            for (int x = 0; x < ctx->N; ++x)
+                for (int y = 0; y <= x; ++y, ++xy) {
+                    const double r = std::sqrt(std::fabs(hd[xy]));
+                    t1 += r;
+                    dm = std::max(dm, r);
+                    rowsum[x] += r;
+                    if (y != x) rowsum[y] += r;
+                }
+            double rmax = 0.0;
+            for (double r : rowsum) rmax = std::max(rmax, r);
+            ctx->det_bound_jk = 1.5 * (2.0 * dm * t1 + 2.0 * rmax * rmax);
+        }
         float ms = 0;
         cudaEventElapsedTime(&ms, ctx->ev[EV_A], ctx->ev[EV_B]);
         ctx->timings[0] = ms;
@@ -524,6 +552,22 @@ int fock_eri_export_packed(fock_ctx *ctx, double *host, size_t n) {
     }
     FOCK_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(host, ctx->d_V, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return FOCK_OK;
+}
+
+int fock_diagonal_export(fock_ctx *ctx, double *host, size_t n) {
+    if (!ctx || !host) return FOCK_ERR_BAD_ARG;
+    if (n != ctx->npair) {
+        ctx->err = "export size must be N(N+1)/2";
+        return FOCK_ERR_BAD_ARG;
+    }
+    if (!ctx->built) {
+        ctx->err = "fock_diagonal_export before fock_eri_build";
+        return FOCK_ERR_STATE;
+    }
+    FOCK_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(host, ctx->d_diag, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return FOCK_OK;
 }
@@ -631,15 +675,36 @@ int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev) {
         // the class kernels digest shell blocks into the full matrix A (BlockDirectSink); the general paths
         // below still digest integral by integral into the packed y; combine_g_kernel adds the two
         const unsigned nn_blocks = (unsigned)(((size_t)ctx->N * ctx->N + 255) / 256);
+        double fx_scale = 0.0;
+        if (ctx->opts.deterministic) {
+            // fixed-point scale: the largest power of two that keeps every partial sum of A inside 62 bits
+            if (cs->sq.enabled || !cs->all_covered) {
+                ctx->err = "deterministic mode needs a basis the class kernels cover entirely (s, p, d shells)";
+                return FOCK_ERR_UNSUPPORTED;
+            }
+            if (!ctx->d_det) FOCK_CUDA_TRY(ctx, cudaMalloc((void **)&ctx->d_det, 2 * sizeof(double)));
+            FOCK_CUDA_TRY(ctx, cudaMemsetAsync(ctx->d_det, 0, 2 * sizeof(double), st));
+            max_abs_kernel<<<64, 256, 0, st>>>(D_dev, (size_t)ctx->N * ctx->N, reinterpret_cast<unsigned long long *>(ctx->d_det));
+            double dmax = 0.0;
+            FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(&dmax, ctx->d_det, sizeof(double), cudaMemcpyDeviceToHost, st));
+            FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+            double bound = dmax * ctx->det_bound_jk;
+            if (!(bound > 0.0) || !std::isfinite(bound)) bound = 1.0;
+            int e = 0;
+            std::frexp(bound, &e);  // bound < 2^e
+            fx_scale = std::ldexp(1.0, 62 - e);
+            ctx->det_scale = fx_scale;
+            launches += 1;
+        }
         symm_density_kernel<<<nn_blocks, 256, 0, st>>>(D_dev, ctx->N, ctx->d_Ds, ctx->d_A);
         diag_digest_block_kernel<<<(unsigned)((ctx->npair + 255) / 256), 256, 0, st>>>(ctx->d_diag, ctx->npair, ctx->opts.rank,
-                                                                                     ctx->opts.world, ctx->d_Ds, ctx->N, ctx->d_A);
+                                                                                     ctx->opts.world, ctx->d_Ds, ctx->N, ctx->d_A, fx_scale);
         launches += 3;
         if (!ctx->shells.pairs.empty()) {
             std::string err;
             FOCK_TRY(make_plan_timed(ctx, thr, ctx->opts.rank, ctx->opts.world));
             FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_k0, st));
-            BlockDirectSink sink{ctx->d_A, ctx->d_Ds, ctx->d_diag, thr, ctx->opts.screen, ctx->N};
+            BlockDirectSink sink{ctx->d_A, ctx->d_Ds, ctx->d_diag, thr, ctx->opts.screen, ctx->N, fx_scale};
             const int l = cs->engine.run_plan(sink, err);
             FOCK_CUDA_TRY(ctx, cudaEventRecord(cs->ev_k1, st));
             if (l < 0) {
@@ -667,10 +732,26 @@ int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev) {
                 ctx->opts.rank, ctx->opts.world, ctx->d_dvec, ctx->d_yvec);
             launches += 1;
         }
-        combine_g_kernel<<<nn_blocks, 256, 0, st>>>(ctx->d_yvec, ctx->d_A, ctx->N, G_dev);
+        // deterministic mode sums the fixed-point partials of all ranks as integers (exact), then converts once
+        if (fx_scale != 0.0 && ctx->comm) {
+            FOCK_TRY(fock_comm_allreduce(ctx, ctx->d_A, (size_t)ctx->N * ctx->N, true, st));
+            launches += 1;
+        }
+        combine_g_kernel<<<nn_blocks, 256, 0, st>>>(ctx->d_yvec, ctx->d_A, ctx->N, G_dev, fx_scale != 0.0 ? 1.0 / fx_scale : 0.0);
         launches += 1;
+        if (fx_scale != 0.0 && ctx->comm) {
+            FOCK_CUDA_TRY(ctx, cudaGetLastError());
+            FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_F], st));
+            ctx->stats[7] = launches;
+            return FOCK_OK;
+        }
     }
     FOCK_CUDA_TRY(ctx, cudaGetLastError());
+    // the one exchange step of the path: partial G of every rank summed over NVLink (no-op without a communicator)
+    if (ctx->comm) {
+        FOCK_TRY(fock_comm_allreduce(ctx, G_dev, (size_t)ctx->N * ctx->N, false, st));
+        launches += 1;
+    }
     FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_F], st));
     ctx->stats[7] = launches;
     return FOCK_OK;

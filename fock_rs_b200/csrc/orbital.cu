@@ -210,15 +210,15 @@ extern "C" int fock_orbital_voxelize(fock_ctx *ctx, const double *coeff, double 
     FOCK_TRY(upload_plan(ctx, grp, fns, d));
     FOCK_CUDA_TRY(ctx, cudaMalloc(&d.out, n * sizeof(float)));
     cudaStream_t st = ctx->stream;
-    FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_E], st));
+    FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_ORB0], st));
     orbital_voxel_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.grp, (int)grp.size(), d.fns, ctx->d_exp, ctx->d_coef, n_voxels, box_size,
                                                                      n, (float *)d.out);
     FOCK_CUDA_TRY(ctx, cudaGetLastError());
-    FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_F], st));
+    FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_ORB1], st));
     FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(grid, d.out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
     FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
     float ms = 0.f;
-    cudaEventElapsedTime(&ms, ctx->ev[EV_E], ctx->ev[EV_F]);
+    cudaEventElapsedTime(&ms, ctx->ev[EV_ORB0], ctx->ev[EV_ORB1]);
     ctx->orbital_ms = ms;
     ctx->orbital_groups = (int)grp.size();
     ctx->orbital_functions = (int)fns.size();

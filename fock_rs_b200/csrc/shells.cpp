@@ -64,7 +64,9 @@ bool build_shells(int n, const double *center, const int32_t *angular, const int
             for (int i = 0; ok && i < np; ++i) ok = same_bits(out.exps[s.prim_begin + i], fe[i]);
             // one radial coefficient list per shell: a component may differ from it by a constant factor
             // (Cartesian d components differ by the sqrt(3) norm ratio, basis/src/primitives.rs:19-27);
-            // the ratio must be the same for every primitive to within a few ulps
+            // the ratio must be the same for every primitive to within the rounding of the two norm chains
+            // (sqrt((8a)^2/12) against sqrt((8a)^2/4), the c*norm products and the division: ~16 ulp worst case;
+            // the bound is 32 ulp so that a legitimate Cartesian d shell is never split into partial shells)
             double ratio = 1.0;
             if (ok) {
                 const double r0 = out.coefs[s.prim_begin];
@@ -72,7 +74,7 @@ bool build_shells(int n, const double *center, const int32_t *angular, const int
                 if (ok) ratio = fc[0] / r0;
                 for (int i = 0; ok && i < np; ++i) {
                     const double want = ratio * out.coefs[s.prim_begin + i];
-                    ok = std::fabs(fc[i] - want) <= 8e-16 * std::fabs(want);
+                    ok = std::fabs(fc[i] - want) <= 4e-15 * std::fabs(want);
                 }
                 bool identical = true;
                 for (int i = 0; identical && i < np; ++i) identical = same_bits(out.coefs[s.prim_begin + i], fc[i]);
@@ -107,8 +109,14 @@ bool build_shells(int n, const double *center, const int32_t *angular, const int
     }
     out.all_class_ok = true;
     out.n_class_shells = 0;
+    out.n_partial_shells = 0;
     for (const Shell &s : out.shells) {
         if (s.class_ok) ++out.n_class_shells; else out.all_class_ok = false;
+        if (s.L <= 2) {  // an s/p/d shell that did not collect all its Cartesian components (reported in fock_stats[12])
+            int have = 0;
+            for (int c = 0; c < 6; ++c) have += s.bf[c] >= 0;
+            if (have != (s.L + 1) * (s.L + 2) / 2) ++out.n_partial_shells;
+        }
     }
     return true;
 }

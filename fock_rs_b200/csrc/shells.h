@@ -66,6 +66,7 @@ struct ShellData {
     std::vector<Sublist> sublists;
     bool all_class_ok = false;           // every function sits in a class-eligible shell
     int n_class_shells = 0;
+    int n_partial_shells = 0;  // s/p/d shells missing Cartesian components (fragmented by the regrouping)
     std::string describe() const;
 };
 

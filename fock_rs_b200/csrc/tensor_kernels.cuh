@@ -96,8 +96,16 @@ __global__ void symm_density_kernel(const double *__restrict__ D, int n, double 
 }
 
 // the diagonal integrals (xy|xy) in the same weighted form: w = v (x==y ? 1/4 : 1) / 2
+// (fx_scale != 0: A holds 64-bit fixed-point integers, deterministic mode -- see BlockDirectSink::add)
+__device__ __forceinline__ void acc_add(double *p, double v, double fx_scale) {
+    if (fx_scale != 0.0)
+        atomicAdd(reinterpret_cast<unsigned long long *>(p), (unsigned long long)__double2ll_rn(v * fx_scale));
+    else
+        atomicAdd(p, v);
+}
+
 __global__ void diag_digest_block_kernel(const double *__restrict__ diag, size_t npair, int rank, int world,
-                                         const double *__restrict__ Ds, int n, double *__restrict__ A) {
+                                         const double *__restrict__ Ds, int n, double *__restrict__ A, double fx_scale) {
     const size_t xy = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (xy >= npair || (int)(xy % (size_t)world) != rank) return;
     size_t x, y;
@@ -106,18 +114,38 @@ __global__ void diag_digest_block_kernel(const double *__restrict__ diag, size_t
     if (w == 0.0) return;
     const size_t N = (size_t)n;
     const double Dxy = Ds[x * N + y];
-    atomicAdd(A + x * N + y, 4.0 * w * Dxy - 0.5 * w * Dxy);  // both Coulomb terms and the (xy|yx) exchange term
-    atomicAdd(A + y * N + x, -0.5 * w * Dxy);
-    atomicAdd(A + x * N + x, -0.5 * w * Ds[y * N + y]);
-    atomicAdd(A + y * N + y, -0.5 * w * Ds[x * N + x]);
+    acc_add(A + x * N + y, 4.0 * w * Dxy - 0.5 * w * Dxy, fx_scale);  // both Coulomb terms and the (xy|yx) exchange term
+    acc_add(A + y * N + x, -0.5 * w * Dxy, fx_scale);
+    acc_add(A + x * N + x, -0.5 * w * Ds[y * N + y], fx_scale);
+    acc_add(A + y * N + y, -0.5 * w * Ds[x * N + x], fx_scale);
+}
+
+// max |v| over a device array as the bit pattern of a non-negative double (they order like integers); NaN -> +inf
+__global__ void max_abs_kernel(const double *__restrict__ v, size_t n, unsigned long long *__restrict__ out) {
+    double m = 0.0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double a = fabs(v[i]);
+        if (!(a <= m)) m = (a == a) ? a : __longlong_as_double(0x7ff0000000000000LL);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
 }
 
 // G (column-major N x N) = packed y (general-path contributions) + A + A^T
-__global__ void combine_g_kernel(const double *__restrict__ y, const double *__restrict__ A, int n, double *__restrict__ G) {
+// (inv_scale != 0: A holds fixed-point integers; the two triangles are added as integers, then scaled -- exact)
+__global__ void combine_g_kernel(const double *__restrict__ y, const double *__restrict__ A, int n, double *__restrict__ G, double inv_scale) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)n * n) return;
     const size_t i = idx % n, j = idx / n;
-    G[idx] = y[i >= j ? tri(i, j) : tri(j, i)] + (A[i * (size_t)n + j] + A[j * (size_t)n + i]);  // exactly symmetric
+    double a;
+    if (inv_scale != 0.0) {
+        const long long *Ai = reinterpret_cast<const long long *>(A);
+        a = (double)(Ai[i * (size_t)n + j] + Ai[j * (size_t)n + i]) * inv_scale;
+    } else {
+        a = A[i * (size_t)n + j] + A[j * (size_t)n + i];
+    }
+    G[idx] = y[i >= j ? tri(i, j) : tri(j, i)] + a;  // exactly symmetric
 }
 
 // ---- batch of arbitrary function quartets (fock_eri_batch)

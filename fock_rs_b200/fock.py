@@ -36,7 +36,7 @@ class FockBuilder:
     """Owns one `fock_ctx`.  Options mirror `fock_opts` (include/fock_b200.h)."""
 
     def __init__(self, basis, mode=_lib.MODE_FAITHFUL, screen=_lib.SCREEN_REFERENCE, tau=1e-6, storage=_lib.STORAGE_INCORE,
-                 device=-1, rank=0, world=1, keep_eri=True, kernel=0, incore_shard=0):
+                 device=-1, rank=0, world=1, keep_eri=True, kernel=0, incore_shard=0, deterministic=False):
         self._L = _lib.load()
         self._ctx = C.c_void_p()
         flat = _as_flat(basis)
@@ -54,6 +54,7 @@ class FockBuilder:
         opts.mode, opts.screen, opts.tau, opts.storage = int(mode), int(screen), float(tau), int(storage)
         opts.device, opts.rank, opts.world, opts.keep_eri, opts.kernel = int(device), int(rank), int(world), int(bool(keep_eri)), int(kernel)
         opts.incore_shard = int(incore_shard)
+        opts.deterministic = int(bool(deterministic))
         self.opts = opts
         st = self._L.fock_create(C.byref(cb), C.byref(opts), C.byref(self._ctx))
         if st != _lib.OK:
@@ -99,6 +100,41 @@ class FockBuilder:
         out = np.empty(self._L.fock_packed_len(self.n), dtype=np.float64)
         self._check(self._L.fock_eri_export_packed(self._ctx, _dp(out), out.size))
         return out
+
+    def diagonal_export(self) -> np.ndarray:
+        """The `diagonal` vector of ElectronTensor::from_basis (basis/src/electron_tensor.rs:90-101): (xy|xy) at tri(x,y)."""
+        out = np.empty(self.n * (self.n + 1) // 2, dtype=np.float64)
+        self._check(self._L.fock_diagonal_export(self._ctx, _dp(out), out.size))
+        return out
+
+    # -- the exchange step behind the ABI (fock_comm_*): after comm_init, build_g returns the complete G on every rank
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        L = _lib.load()
+        buf = C.create_string_buffer(_lib.COMM_ID_BYTES)
+        st = L.fock_comm_unique_id(buf)
+        if st != _lib.OK:
+            msg = L.fock_comm_last_error()
+            raise FockError(st, msg.decode() if msg else "fock_comm_unique_id failed")
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes):
+        if len(unique_id) != _lib.COMM_ID_BYTES:
+            raise ValueError("the communicator id has FOCK_COMM_ID_BYTES bytes")
+        self._check(self._L.fock_comm_init(self._ctx, unique_id))
+        return self
+
+    def comm_init_torch(self):
+        """Under torch.distributed (any backend): rank 0 creates the id, the process group broadcasts it."""
+        import torch.distributed as dist
+
+        box = [self.comm_unique_id() if dist.get_rank() == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return self.comm_init(box[0])
+
+    @property
+    def comm_attached(self) -> bool:
+        return bool(self._L.fock_comm_attached(self._ctx))
 
     def eri_batch(self, quartets) -> np.ndarray:
         q = np.ascontiguousarray(quartets, dtype=np.int32).reshape(-1, 4)
@@ -191,6 +227,7 @@ class FockBuilder:
             "n_basis": s[0], "shells": s[1], "shell_pairs": s[2], "shell_quartets_unique": s[3],
             "shell_quartets_evaluated": s[4], "prim_quartets_evaluated": s[5], "launches_build": s[6],
             "launches_g": s[7], "model_flops": s[8], "generic_integrals_evaluated": s[9], "warp_tiles": s[10], "general_shell_quartets_evaluated": s[11],
+            "partial_shells": s[12],
         }
 
 
@@ -255,8 +292,11 @@ class FockEngine:
     """The engine `try_scf` drives (see fock_rs_b200.scf).  Rank/world come from torch.distributed
     when it is initialised; partial G matrices are all-reduced over NCCL."""
 
-    def __init__(self, mode=_lib.MODE_FAITHFUL, screen=_lib.SCREEN_REFERENCE, tau=1e-6, storage=_lib.STORAGE_INCORE, device=-1, distributed=None):
-        self.kw = dict(mode=mode, screen=screen, tau=tau, storage=storage, device=device)
+    def __init__(self, mode=_lib.MODE_FAITHFUL, screen=_lib.SCREEN_REFERENCE, tau=1e-6, storage=_lib.STORAGE_INCORE, device=-1, distributed=None,
+                 keep_eri=False, deterministic=False):
+        # keep_eri: the SCF loop never reads the raw (ij|kl) tensor (only ElectronTensor / export users do), so the
+        # engine does not hold it: half the HBM footprint and build write traffic of an in-core build
+        self.kw = dict(mode=mode, screen=screen, tau=tau, storage=storage, device=device, keep_eri=keep_eri, deterministic=deterministic)
         self.builder: Optional[FockBuilder] = None
         self._staged = None
         self.rank, self.world = 0, 1
@@ -272,12 +312,26 @@ class FockEngine:
             import torch.distributed as dist
 
             self.rank, self.world = dist.get_rank(), dist.get_world_size()
+            if device < 0:  # one process per GPU: bind to the local rank's device, not whatever happens to be current
+                import os
+
+                try:
+                    import torch
+
+                    self.kw["device"] = int(os.environ.get("LOCAL_RANK", torch.cuda.current_device())) if torch.cuda.is_available() else -1
+                except Exception:
+                    pass
 
     def _ensure(self, flat):
         if self.builder is None or self.builder.flat is not flat:
             if self.builder is not None:
                 self.builder.close()
             self.builder = FockBuilder(flat, rank=self.rank, world=self.world, **self.kw)
+            if self.distributed and self.world > 1:
+                import torch.distributed as dist
+
+                if dist.get_backend() == "nccl":  # the all-reduce then happens inside fock_build_g, on the device
+                    self.builder.comm_init_torch()
         return self.builder
 
     def one_electron(self, flat, nuc_pos, nuc_chg):
@@ -291,12 +345,8 @@ class FockEngine:
         if self.distributed and self.world > 1:
             import torch.distributed as dist
 
-            if dist.get_backend() == "nccl":  # one PCIe round trip, partials summed on the device
-                from .parallel import HostStagedG
-
-                if self._staged is None or self._staged.b is not self.builder:
-                    self._staged = HostStagedG(self.builder)
-                return self._staged(D)
+            if self.builder.comm_attached:  # one PCIe round trip; partials summed over NVLink inside the C ABI call
+                return self.builder.build_g(D)
             from .parallel import allreduce_host_matrix
 
             return allreduce_host_matrix(self.builder.build_g(D))

@@ -108,6 +108,20 @@ class FockBuilder {
         check(fock_orbital_voxelize(ctx_, coeff.data(), min_coeff, n_voxels, box_size, g.data()));
         return g;
     }
+    // The exchange step (fock_comm_*): rank 0 makes an id, every rank attaches; build_g then returns the complete G.
+    static std::array<char, FOCK_COMM_ID_BYTES> comm_unique_id() {
+        std::array<char, FOCK_COMM_ID_BYTES> id{};
+        const int st = fock_comm_unique_id(id.data());
+        if (st != FOCK_OK) throw FockError(st, fock_comm_last_error());
+        return id;
+    }
+    void comm_init(const std::array<char, FOCK_COMM_ID_BYTES> &id) { check(fock_comm_init(ctx_, id.data())); }
+    bool comm_attached() const { return fock_comm_attached(ctx_) != 0; }
+    std::vector<double> diagonal() const {
+        std::vector<double> d((size_t)n_ * (n_ + 1) / 2);
+        check(fock_diagonal_export(ctx_, d.data(), d.size()));
+        return d;
+    }
     fock_ctx *raw() const { return ctx_; }
 
    private:

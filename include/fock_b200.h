@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FOCK_B200_ABI_VERSION 3
+#define FOCK_B200_ABI_VERSION 4
 
 typedef struct fock_ctx fock_ctx;
 
@@ -86,6 +86,10 @@ typedef struct {
     int32_t incore_shard; /* world > 1, in-core: 0 = replicate the build, shard the per-iteration streaming
                              (best when a build is followed by more than ~T_build/T_G iterations);
                              1 = shard the build, every rank streams its own partial supermatrix */
+    int32_t deterministic; /* integral-direct only: 1 = the Fock accumulation runs in 64-bit fixed point (integer
+                              atomics are associative), so G is bit-identical from run to run, for any launch
+                              geometry and any number of ranks; the reference's serial loop (scf/src/lib.rs:177-185)
+                              is deterministic, FP64 atomics are not.  Default 0. */
 } fock_opts;
 
 void fock_default_opts(fock_opts *opts);
@@ -122,10 +126,16 @@ int fock_eri_batch(fock_ctx *ctx, const int32_t *quartets, size_t n, double *val
  * through the generic evaluator.  order > 10 -> FOCK_ERR_BOYS_ORDER (the reference asserts). */
 int fock_boys_batch(fock_ctx *ctx, const double *t, size_t n, int32_t order, double *values);
 
+/* The `diagonal` vector of ElectronTensor::from_basis (basis/src/electron_tensor.rs:90-101): (xy|xy) for every
+ * x >= y at slot tri(x,y), the screening estimates of the cut.  `n` must equal N(N+1)/2; after fock_eri_build. */
+int fock_diagonal_export(fock_ctx *ctx, double *host, size_t n);
+
 /* The per-iteration G build, scf/src/lib.rs:177-185 (inside utils::hermitian, scf/src/utils.rs:25-28):
  *   G_ij = sum_xy D[(x,y)] * ((ij|xy) - 1/2 (ix|jy)),   G symmetric.
- * D must be symmetric (the reference's density is, by construction).  With world > 1 the
- * result is this rank's PARTIAL G; the caller sums partials (one all-reduce of N*N doubles). */
+ * D must be symmetric (the reference's density is, by construction).  With world > 1 and a communicator
+ * attached (fock_comm_init) the result is the COMPLETE G on every rank -- the partial matrices are summed by
+ * one NCCL all-reduce of N*N doubles on the context's stream, inside this call; without a communicator it is
+ * this rank's PARTIAL G and the caller sums the partials. */
 int fock_build_g(fock_ctx *ctx, const double *D, double *G);
 
 /* Same with device-resident D and G (N*N doubles each) on the context's stream. */
@@ -168,6 +178,19 @@ int fock_set_stream(fock_ctx *ctx, void *cuda_stream);
 int fock_supermatrix_device(fock_ctx *ctx, void **dev_ptr, size_t *n_elements);
 int fock_set_digest_range(fock_ctx *ctx, size_t begin, size_t end);
 
+/* The exchange step behind the ABI (nothing in the reference -- its try_scf is one process).
+ * One process (or thread) per GPU, each with its own context created with the same basis/options and its
+ * rank/world.  Rank 0 obtains an id, the host ships those FOCK_COMM_ID_BYTES bytes to the other ranks by any means it
+ * has, and EVERY rank calls fock_comm_init (collective: it returns when all ranks have joined).  From then on
+ * fock_build_g / fock_build_g_device return the complete G on every rank.  NCCL is loaded at run time
+ * (libnccl.so.2; FOCK_NCCL_LIB overrides the name); FOCK_ERR_UNSUPPORTED if it cannot be found. */
+#define FOCK_COMM_ID_BYTES 128
+int fock_comm_unique_id(void *id_out);
+int fock_comm_init(fock_ctx *ctx, const void *id);
+int fock_comm_destroy(fock_ctx *ctx);   /* also done by fock_destroy */
+int fock_comm_attached(fock_ctx *ctx);  /* 1 if fock_build_g returns the complete G */
+const char *fock_comm_last_error(void); /* for fock_comm_unique_id, which has no context */
+
 /* Timings of the last fock_eri_build / fock_build_g in milliseconds (CUDA events):
  *   [0] pair/diagonal pass  [1] tensor build after the diagonal launch (memsets, host sort/plan, class kernels)  [2] supermatrix gather (kernel=1 only)
  *   [3] last G build (device part)  [4] last G build incl. host<->device copies
@@ -180,7 +203,9 @@ int fock_timings(fock_ctx *ctx, double *ms, int32_t n);
  *   [6] kernel launches of the last fock_eri_build  [7] kernel launches of the last fock_build_g
  *   [8] model FP64 flops of the class quartets evaluated (SURVEY.md section 8d formula)
  *   [9] integrals evaluated by the per-function generic kernel  [10] warp tiles of the class launches
- *   [11] shell quartets evaluated by the general shell-quartet kernel (irregular shells; d shells with kernel = 2) */
+ *   [11] shell quartets evaluated by the general shell-quartet kernel (irregular shells; d shells with kernel = 2)
+ *   [12] s/p/d shells that came out of the regrouping with Cartesian components missing (0 for every shipped basis:
+ *        results are right either way, but fragmented d shells run far below the class kernels' speed) */
 int fock_stats(fock_ctx *ctx, int64_t *out, int32_t n);
 
 /* Measurement aid (no reference counterpart): sustained FP64 FMA rate of this GPU from a

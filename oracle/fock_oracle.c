@@ -310,7 +310,20 @@ static void r_table(int T, int U, int V, double alpha, const double diff[3], dou
     static _Thread_local double R[RDIM][TMAX][TMAX][TMAX]; /* [n][t][u][v] */
     int L = T + U + V;
     if (L > 10) L = 10;
-    for (int n = 0; n <= L; ++n) R[n][0][0][0] = powi(-2.0 * alpha, n) * boys_sel(alpha * dist_sq, n, flags);
+    if (flags & ORACLE_BOYS_EXACT) {
+        /* accurate mode (not in the reference): one series evaluation at the top order, then the
+         * downward recursion F_{n-1} = (2T F_n + e^-T)/(2n-1), which is stable in this direction --
+         * the same values as oracle_boys_exact(T, n) per order to rounding, at 1/(L+1) of the cost
+         * (this is what makes the full-size golden G matrices of tools/make_golden_large.py affordable) */
+        const double tt = alpha * dist_sq;
+        double f[RDIM];
+        f[L] = oracle_boys_exact(tt, L);
+        const double e = exp(-tt);
+        for (int n = L; n >= 1; --n) f[n - 1] = (2.0 * tt * f[n] + e) / (double)(2 * n - 1);
+        for (int n = 0; n <= L; ++n) R[n][0][0][0] = powi(-2.0 * alpha, n) * f[n];
+    } else {
+        for (int n = 0; n <= L; ++n) R[n][0][0][0] = powi(-2.0 * alpha, n) * boys_sel(alpha * dist_sq, n, flags);
+    }
     for (int v = 1; v <= V; ++v)
         for (int n = 0; n + v <= L; ++n)
             R[n][0][0][v] = diff[2] * R[n + 1][0][0][v - 1] + (v > 1 ? (double)(v - 1) * R[n + 1][0][0][v - 2] : 0.0);
@@ -531,6 +544,83 @@ void oracle_build_g(const double *packed, int n_basis, const double *D, double *
             G[j + (size_t)i * n] = acc;
         }
     }
+}
+
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* The same tensor build + G loop in integral-direct form, for sizes whose N^4 (or packed) tensor does
+ * not fit anywhere: every canonical slot (xy >= zw) of basis/src/electron_tensor.rs:113-158 is visited
+ * once, its value decided exactly as there (diagonal slots always evaluated, :90-101; the others
+ * `estimate > 1e-6 ? ERI : 0.0`, :129-158), and digested straight into G by the definition of
+ * scf/src/lib.rs:167-185: with v = (ab|cd), every DISTINCT ordered image (p,q,r,s) of (a,b,c,d) under
+ * the 8 index permutations the reference's IntegralIndex folds together (:37-51) is one term
+ * (pq|rs) of the dense tensor, contributing  J[p,q] += D[r,s] v  (the (ij|xy) term, i=p j=q x=r y=s)
+ * and  K[p,r] += D[q,s] v  (the (ix|jy) term, i=p x=q j=r y=s);  G = J - K/2.  D must be symmetric
+ * (the reference mirrors the i<=j triangle, which is only consistent for symmetric D).  Summation order
+ * differs from the dense loop, i.e. agreement with oracle_build_g is to rounding (tests/test_oracle.py).
+ * Rows xy = row_start, row_start+row_stride, ... (at most max_rows of them; row_stride = 1, row_start = 0,
+ * max_rows >= np is the whole job) so that the CPU baseline can time a bounded sample of the same loop.
+ * Returns the number of integrals evaluated (diagonal ones included). */
+int64_t oracle_direct_g(const oracle_basis *bs, int flags, int fast, const double *diag, const double *D, double *G,
+                        int64_t row_start, int64_t row_stride, int64_t max_rows) {
+    const size_t n = (size_t)bs->n_basis;
+    const size_t np = n * (n + 1) / 2;
+    int32_t *px = (int32_t *)malloc(sizeof(int32_t) * np), *py = (int32_t *)malloc(sizeof(int32_t) * np);
+    for (size_t x = 0; x < n; ++x)
+        for (size_t y = 0; y <= x; ++y) {
+            px[tri(x, y)] = (int32_t)x;
+            py[tri(x, y)] = (int32_t)y;
+        }
+    int64_t nrows = 0;
+    for (int64_t xy = row_start; xy < (int64_t)np && nrows < max_rows; xy += row_stride) ++nrows;
+    int64_t evaluated = 0;
+    memset(G, 0, sizeof(double) * n * n);
+#pragma omp parallel reduction(+ : evaluated)
+    {
+        double *J = (double *)calloc(n * n, sizeof(double)), *K = (double *)calloc(n * n, sizeof(double));
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t r = nrows - 1; r >= 0; --r) {
+            const int64_t xy = row_start + r * row_stride;
+            const int a = px[xy], b = py[xy];
+            for (int64_t zw = 0; zw <= xy; ++zw) {
+                const int c = px[zw], d = py[zw];
+                double v;
+                if (zw == xy) {
+                    v = diag[xy];
+                } else {
+                    double estimate = sqrt(diag[xy] * diag[zw]);
+                    if (!((flags & ORACLE_NO_CUT) || estimate > 1e-6)) continue; /* slot holds 0.0 */
+                    v = eri_sel(bs, a, b, c, d, flags, fast);
+                }
+                evaluated += 1;
+                const int img[8][4] = {{a, b, c, d}, {b, a, c, d}, {a, b, d, c}, {b, a, d, c},
+                                       {c, d, a, b}, {d, c, a, b}, {c, d, b, a}, {d, c, b, a}};
+                for (int m = 0; m < 8; ++m) {
+                    int dup = 0;
+                    for (int e = 0; e < m && !dup; ++e)
+                        dup = img[e][0] == img[m][0] && img[e][1] == img[m][1] && img[e][2] == img[m][2] &&
+                              img[e][3] == img[m][3];
+                    if (dup) continue;
+                    const size_t p = (size_t)img[m][0], q = (size_t)img[m][1], rr = (size_t)img[m][2], s = (size_t)img[m][3];
+                    J[p + q * n] += D[rr + s * n] * v;
+                    K[p + rr * n] += D[q + s * n] * v;
+                }
+            }
+        }
+#pragma omp critical
+        for (size_t i = 0; i < n * n; ++i) G[i] += J[i] - 0.5 * K[i];
+        free(J);
+        free(K);
+    }
+    free(px);
+    free(py);
+    return evaluated;
 }
 
 /* ------------------------------------------------------------------ one-electron integrals

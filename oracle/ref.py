@@ -67,6 +67,10 @@ def lib():
         L.oracle_sample_rows.argtypes = [bp, C.c_int, C.c_int, dp, C.c_int64, C.c_int64, C.c_int64, dp]
         L.oracle_diagonal.restype = None
         L.oracle_diagonal.argtypes = [bp, C.c_int, C.c_int, dp]
+        L.oracle_set_num_threads.restype = None
+        L.oracle_set_num_threads.argtypes = [C.c_int]
+        L.oracle_direct_g.restype = C.c_int64
+        L.oracle_direct_g.argtypes = [bp, C.c_int, C.c_int, dp, dp, dp, C.c_int64, C.c_int64, C.c_int64]
         L.oracle_build_g.restype = None
         L.oracle_build_g.argtypes = [dp, C.c_int, dp, dp, C.c_int]
         L.oracle_one_electron.restype = None
@@ -145,6 +149,27 @@ def packed_len(n):
 
 def num_threads():
     return lib().oracle_num_threads()
+
+
+def set_num_threads(n):
+    """OpenMP threads of the oracle's parallel loops (torchrun exports OMP_NUM_THREADS=1)."""
+    lib().oracle_set_num_threads(int(n))
+
+
+def direct_g(ob, D, flags=0, fast=True, diag=None, row_start=0, row_stride=1, max_rows=None):
+    """Tensor build + G loop in integral-direct form (no N^4 storage); the whole job by default, or the
+    canonical rows row_start, row_start+row_stride, ...  Returns (G, n_evaluated).  D must be symmetric."""
+    n = ob.n
+    Dc = np.asfortranarray(D, dtype=np.float64)
+    assert np.array_equal(Dc, Dc.T), "direct_g needs a symmetric density"
+    if diag is None:
+        diag = diagonal(ob, flags, fast)
+    d = np.ascontiguousarray(diag, dtype=np.float64)
+    G = np.zeros((n, n), dtype=np.float64, order="F")
+    npair = n * (n + 1) // 2
+    nev = lib().oracle_direct_g(C.byref(ob.c), flags, int(fast), _dp(d), _dp(Dc), _dp(G), int(row_start), int(row_stride),
+                                int(npair if max_rows is None else max_rows))
+    return np.array(G), int(nev)
 
 
 def from_basis_packed(ob, flags=0, fast=True):

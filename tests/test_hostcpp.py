@@ -18,7 +18,7 @@ def _compile():
     os.makedirs(os.path.dirname(EXE), exist_ok=True)
     lib_dir = os.path.dirname(_lib.LIB_PATH)
     subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-std=c++17", "-O1", os.path.join(ROOT, "tests", "hostcpp_main.cpp"),
-                           "-o", EXE, "-L" + lib_dir, "-lfock_b200", "-Wl,-rpath," + lib_dir, "-Wl,-rpath,/usr/local/cuda/lib64"])
+                           "-o", EXE, "-pthread", "-L" + lib_dir, "-lfock_b200", "-Wl,-rpath," + lib_dir, "-Wl,-rpath,/usr/local/cuda/lib64"])
 
 
 def test_hostcpp_compiles_and_links():
@@ -48,3 +48,20 @@ def test_hostcpp_matches_oracle():
     np.testing.assert_allclose(psi[:2], want_psi, rtol=0, atol=1e-13)
     grid = oracle.voxelize(ob, c, 2, 4.0)
     np.testing.assert_allclose(psi[2:], [grid[0], grid[7]], rtol=1e-6, atol=0)
+
+
+@pytest.mark.gpu
+def test_hostcpp_two_gpus_complete_g_through_the_abi():
+    """The collective behind the C ABI, driven from compiled host code only: 2 threads / 2 GPUs / one NCCL
+    communicator attached with fock_comm_init; every rank's fock_build_g returns the complete G."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _compile()
+    out = subprocess.run([EXE, "multi", "2"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    tag, d1, dr = out.stdout.strip().splitlines()[-1].split()
+    assert tag == "MULTI_OK"
+    assert float(d1) <= 1e-11  # same integrals, different summation order
+    assert float(dr) == 0.0    # every rank holds the same all-reduced matrix

@@ -7,8 +7,8 @@ O=gpurun_out/variants.log
 : > $O
 for lib in default $(ls build/var/libfock_*.so 2>/dev/null); do
   if [ "$lib" = default ]; then unset FOCK_B200_LIB; else export FOCK_B200_LIB=$PWD/$lib; fi
-  for cfg in "alkane40 6-31G 0 1" "w16 6-31G 0 0" "benzene 6-31G 0 0"; do
-    for rep in 1 2; do TAG=$(basename $lib) timeout 120 python tools/time_config.py $cfg 2>&1 | head -1 >> $O; done
+  for cfg in "alkane40 6-31G 0 1" "w16 6-31G 0 0" "w16 6-31G 1 1" "w32 cc-pVDZ 0 1"; do
+    TAG=$(basename $lib) timeout 300 python tools/time_config.py $cfg 2>&1 | head -1 >> $O   # min / median of 6 G builds inside
   done
 done
 cat $O
