@@ -2,6 +2,7 @@
 // (device-side permutation of the primitive-pair tables), the job / warp-tile plan, kernel dispatch.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <numeric>
 
@@ -19,7 +20,7 @@ namespace {
 template <int LA, int LB, int LC, int LD, int KC0, int KCN, class Sink>
 void launch_mode(const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, cudaStream_t st) {
     constexpr int NAB = ncart_c(LA) * ncart_c(LB);
-    const size_t smem = boys_smem_bytes(LA + LB + LC + LD, cl.boys_ni) + near_queue_smem_bytes(LA, LB, LC, LD, NAB * KCN);
+    const size_t smem = boys_smem_bytes(LA + LB + LC + LD, cl.boys_ni);
     if (mode & FOCK_MODE_FIX_R_BIT)
         eri_class_kernel<LA, LB, LC, LD, 1, 0, NAB, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
     else
@@ -197,29 +198,19 @@ int ClassEngine::upload_master(std::string &err) {
         cudaMemcpy(d_iota, iota.data(), iota.size() * sizeof(int), cudaMemcpyHostToDevice);
         cudaMemcpy(d_seg, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice);
         sort_temp_bytes = 0;
-        cub::DeviceSegmentedSort::SortPairsDescending(nullptr, sort_temp_bytes, d_maxdiag, d_keys_sorted, d_iota, d_perm, npairs, nseg,
-                                                      d_seg, d_seg + nseg, stream);
+        cudaGetLastError();  // the size query reports any error left pending on this thread as its own
+        if ((e = cub::DeviceSegmentedSort::SortPairsDescending(nullptr, sort_temp_bytes, d_maxdiag, d_keys_sorted, d_iota, d_perm, npairs, nseg,
+                                                               d_seg, d_seg + nseg, stream)) != cudaSuccess) {
+            err = std::string("sort scratch query: ") + cudaGetErrorString(e);
+            return 1;
+        }
         if ((e = cudaMalloc(&d_sort_temp, sort_temp_bytes + 16)) != cudaSuccess) {
             err = std::string("sort scratch: ") + cudaGetErrorString(e);
             return 1;
         }
     }
-    // the Boys tables in the staged layout of every total angular momentum, in global memory
-    if ((e = cudaMalloc((void **)&d_boys_stage, (boys_stage_off(9, boys_ni) + 8) * sizeof(double))) != cudaSuccess) {
-        err = std::string("Boys stage image: ") + cudaGetErrorString(e);
-        return 1;
-    }
-    boys_stage_kernel<0><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
-    boys_stage_kernel<1><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
-    boys_stage_kernel<2><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
-    boys_stage_kernel<3><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
-    boys_stage_kernel<4><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
-    boys_stage_kernel<5><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
-    boys_stage_kernel<6><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
-    boys_stage_kernel<7><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
-    boys_stage_kernel<8><<<1, 256, 0, stream>>>(d_boys_stage, boys_poly, boys_ni);
-    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) {
-        err = std::string("Boys stage image: ") + cudaGetErrorString(e);
+    if ((e = cudaMalloc((void **)&d_tile_counters, (size_t)kNumPairClasses * kNumPairClasses * kTileCounterSlots * sizeof(unsigned long long))) != cudaSuccess) {
+        err = std::string("tile counters: ") + cudaGetErrorString(e);
         return 1;
     }
     plan_valid = false;
@@ -236,7 +227,7 @@ int ClassEngine::run_diagonal(double *d_diag, std::string &err) {
         const Sublist &s = sd->sublists[si];
         const int n = (int)s.pair_ids.size();
         if (!n) continue;
-        DiagLaunch dl{d_bra_nat + s.bra_off, d_meta_nat + s.meta_off, dev->d_shell_bf, boys_poly, boys_ni, s.K, n, (int)(s.meta_off / 2), d_boys_stage};
+        DiagLaunch dl{d_bra_nat + s.bra_off, d_meta_nat + s.meta_off, dev->d_shell_bf, boys_poly, boys_ni, s.K, n, (int)(s.meta_off / 2)};
         dim3 grid((unsigned)std::min((n + kClassWarps - 1) / kClassWarps, num_sms * 4));
         if (s.cls == 0) {
             launch_diag_mode<0, 0, 0, 1>(dl, sink, mode, grid, stream);
@@ -273,8 +264,11 @@ int ClassEngine::finish_diagonal(const double *d_diag, std::string &err) {
     // like their bit patterns -- and permute the primitive-pair tables accordingly; the host only needs
     // the sorted maxima (for the screening prefixes) and, for the shell-quartet path, the natural ones
     const int nseg = (int)sd->sublists.size();
-    cub::DeviceSegmentedSort::SortPairsDescending(d_sort_temp, sort_temp_bytes, d_maxdiag, d_keys_sorted, d_iota, d_perm, (int)npairs,
-                                                  nseg, d_seg, d_seg + nseg, stream);
+    if (cudaError_t se = cub::DeviceSegmentedSort::SortPairsDescending(d_sort_temp, sort_temp_bytes, d_maxdiag, d_keys_sorted, d_iota, d_perm,
+                                                                       (int)npairs, nseg, d_seg, d_seg + nseg, stream); se != cudaSuccess) {
+        err = std::string("diagonal sort: ") + cudaGetErrorString(se);
+        return -1;
+    }
     if (permute_blocks > 0)
         permute_pairs_kernel<<<permute_blocks, 64, 0, stream>>>(d_permute_desc, permute_count, d_bra_nat, d_meta_nat, d_perm, dev->d_bra, dev->d_ket,
                                                                dev->d_meta);
@@ -434,6 +428,32 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
                     tiles_launch += tiles;
                 }
             }
+            // heaviest tiles first (longest per-lane primitive loop = Kab*Kcd/ksplit): the launch then ends on its cheapest
+            // tiles, which is what bounds the tail of a persistent grid -- most of all when the tile range is 1/8 of the job
+            {
+                static const bool kLpt = !getenv("FOCK_NO_LPT");
+                const int j0 = pl.job_begin, nj = (int)jobs.size() - j0;
+                if (kLpt && nj > 1) {
+                    std::vector<int> order(nj);
+                    std::iota(order.begin(), order.end(), 0);
+                    std::vector<long long> ntiles(nj);
+                    for (int i = 0; i < nj; ++i)
+                        ntiles[i] = (i + 1 < nj ? jobs[j0 + i + 1].tile_begin : tiles_launch) - jobs[j0 + i].tile_begin;
+                    auto cost = [&](int i) { return (double)jobs[j0 + i].Kab * jobs[j0 + i].Kcd / jobs[j0 + i].ksplit; };
+                    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost(a) > cost(b); });
+                    std::vector<ClassJob> sorted_jobs(nj);
+                    std::vector<size_t> sorted_off(nj);
+                    long long tb = 0;
+                    for (int i = 0; i < nj; ++i) {
+                        sorted_jobs[i] = jobs[j0 + order[i]];
+                        sorted_off[i] = job_table_off[j0 + order[i]];
+                        sorted_jobs[i].tile_begin = tb;
+                        tb += ntiles[order[i]];
+                    }
+                    std::copy(sorted_jobs.begin(), sorted_jobs.end(), jobs.begin() + j0);
+                    std::copy(sorted_off.begin(), sorted_off.end(), job_table_off.begin() + j0);
+                }
+            }
             pl.njobs = (int)jobs.size() - pl.job_begin;
             pl.total_tiles = tiles_launch;
             if (pl.njobs > 0) plan.push_back(pl);
@@ -480,7 +500,6 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
         }
         if ((size_t)all_tiles + 1 > tile_tab_cap) {
             if (d_tile_tab) cudaFree(d_tile_tab);
-    if (d_permute_desc) cudaFree(d_permute_desc);
             d_tile_tab = nullptr;
             tile_tab_cap = (size_t)all_tiles + (size_t)all_tiles / 8 + 1024;
             if ((e = cudaMalloc((void **)&d_tile_tab, tile_tab_cap * sizeof(int2))) != cudaSuccess) {
@@ -522,6 +541,8 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
     }
     static const int kStreams = getenv("FOCK_STREAMS") ? std::max(1, std::min(kAuxStreams, atoi(getenv("FOCK_STREAMS")))) : kAuxStreams;
     static const int kBlocksPerSm = getenv("FOCK_BLOCKS_PER_SM") ? atoi(getenv("FOCK_BLOCKS_PER_SM")) : 16;
+    if (kDynTiles)
+        cudaMemsetAsync(d_tile_counters, 0, (size_t)kNumPairClasses * kNumPairClasses * kTileCounterSlots * sizeof(unsigned long long), stream);
     cudaEventRecord(ev_fork, stream);
     for (int i = 0; i < kAuxStreams; ++i) cudaStreamWaitEvent(aux[i], ev_fork, 0);
     int slot = 0;
@@ -536,8 +557,15 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
         cl.fix_r = (mode & FOCK_MODE_FIX_R_BIT) ? 1 : 0;
         cl.boys_poly = boys_poly;
         cl.boys_ni = boys_ni;
-        cl.boys_stage = d_boys_stage;
         cl.tile_tab = d_tile_tab + pl.tile_base;
+        cl.tile_counter = d_tile_counters + (size_t)(pl.cb * kNumPairClasses + pl.ck) * kTileCounterSlots;
+#ifdef FOCK_NEAR_STATS
+        {
+            unsigned long long z[8] = {};
+            cudaDeviceSynchronize();
+            cudaMemcpyToSymbol(g_near_stats, z, sizeof(z));
+        }
+#endif
         cl.rank = plan_rank;
         cl.world = plan_world;
         const long long mine = (pl.total_tiles - plan_rank + plan_world - 1) / plan_world;  // warp tiles of this rank
@@ -559,6 +587,15 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
         }
         launches += l;
         ++slot;
+#ifdef FOCK_NEAR_STATS
+        if (pl.cb < 3) {
+            unsigned long long z[8];
+            cudaDeviceSynchronize();
+            cudaMemcpyFromSymbol(z, g_near_stats, sizeof(z));
+            fprintf(stderr, "NEAR_STATS class(%d|%d) slices %d tiles %llu lanes_active %llu lanes_with_near %llu near_prim %llu prim %llu rounds32 %llu | K>=8: lanes_with_near %llu near_prim %llu\n",
+                    pl.cb, pl.ck, l, z[0], z[5], z[1], z[2], z[3], z[4], z[6], z[7]);
+        }
+#endif
     }
     for (int i = 0; i < kAuxStreams; ++i) {
         cudaEventRecord(ev_join[i], aux[i]);
@@ -577,8 +614,8 @@ template int ClassEngine::run_plan<BlockDirectSink>(const BlockDirectSink &, std
 
 ClassEngine::~ClassEngine() {
     if (d_table) cudaFree(d_table);
-    if (d_boys_stage) cudaFree(d_boys_stage);
     if (d_tile_tab) cudaFree(d_tile_tab);
+    if (d_tile_counters) cudaFree(d_tile_counters);
     if (d_permute_desc) cudaFree(d_permute_desc);
     if (d_shell_scale) cudaFree(d_shell_scale);
     if (d_jobs) cudaFree(d_jobs);

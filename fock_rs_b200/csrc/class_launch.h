@@ -56,7 +56,6 @@ struct ClassEngine {
     PairTablesDev *dev = nullptr;
     const double *boys_poly = nullptr;  // device, per-interval polynomial table of the active mode
     int boys_ni = 200;
-    double *d_boys_stage = nullptr;     // the same tables in the class kernels' staged layout, every L (eri_class.cuh: boys_stage_off)
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     int mode = 0;
@@ -85,6 +84,7 @@ struct ClassEngine {
     double host_ms[4] = {0, 0, 0, 0};  // sort, plan
     ClassJob *d_jobs = nullptr;
     size_t jobs_cap = 0;
+    unsigned long long *d_tile_counters = nullptr;  // [class pairs][kTileCounterSlots], zeroed at the start of every run_plan
     int2 *d_tile_tab = nullptr;  // (job, first row) per warp tile of every launch of the plan
     size_t tile_tab_cap = 0;
     std::vector<ClassPlanLaunch> plan;
