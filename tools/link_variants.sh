@@ -1,10 +1,16 @@
 #!/bin/bash
-# Link build/var/libfock_<name>.so from build/var/class_launch_<name>.o + the other objects of the last full build
-# (run on the GPU box: shipping the objects once is 5x smaller than shipping every variant's 88 MB library).
+# Link build/var/libfock_<name>.so for every variant directory build/var/<name>/ (objects made by tools/build_variants.sh): the
+# variant's objects replace the same-named ones of the last full build (build/obj).  Run on the GPU box: shipping objects
+# is several times smaller than shipping every variant's 88 MB library.
 ROOT=$(cd "$(dirname "$0")/.." && pwd)
-objs=$(ls $ROOT/build/obj/*.o | grep -v class_launch.o)
-for o in $ROOT/build/var/class_launch_*.o; do
-  n=$(basename $o .o); n=${n#class_launch_}
-  /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -shared -o $ROOT/build/var/libfock_$n.so $objs $o -lcudart -ldl || echo "link $n failed"
+for d in $ROOT/build/var/*/; do
+  [ -d "$d" ] || continue
+  n=$(basename $d)
+  objs=""
+  for o in $ROOT/build/obj/*.o; do
+    b=$(basename $o)
+    if [ -f "$d/$b" ]; then objs="$objs $d/$b"; else objs="$objs $o"; fi
+  done
+  /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -shared -o $ROOT/build/var/libfock_$n.so $objs -lcudart -ldl || echo "link $n failed"
 done
 ls -la $ROOT/build/var/*.so
