@@ -575,7 +575,9 @@ def ncu_record(workload, direct, mode):
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             d = json.load(f)
         key = workload + ("/direct" if direct else "/incore")
-        return d.get(key + "/" + mode, d.get(key, {})) or {}
+        rec = dict(d.get(key, {}) or {})
+        rec.update(d.get(key + "/" + mode, {}) or {})
+        return rec
     except (OSError, ValueError):
         return {}
 

@@ -541,7 +541,7 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
     }
     static const int kStreams = getenv("FOCK_STREAMS") ? std::max(1, std::min(kAuxStreams, atoi(getenv("FOCK_STREAMS")))) : kAuxStreams;
     static const int kBlocksPerSm = getenv("FOCK_BLOCKS_PER_SM") ? atoi(getenv("FOCK_BLOCKS_PER_SM")) : 16;
-    if (kDynTiles)
+    if (kDynTilesEnabled)
         cudaMemsetAsync(d_tile_counters, 0, (size_t)kNumPairClasses * kNumPairClasses * kTileCounterSlots * sizeof(unsigned long long), stream);
     cudaEventRecord(ev_fork, stream);
     for (int i = 0; i < kAuxStreams; ++i) cudaStreamWaitEvent(aux[i], ev_fork, 0);

@@ -67,7 +67,9 @@ def allreduce_device(g_tensor):
 
 
 class HostStagedG:
-    """G build for HOST matrices on `world` ranks with ONE PCIe round trip per call: D goes pinned host -> device,
+    """(Superseded by the collective behind the C ABI -- `FockBuilder.comm_init_torch()` makes `build_g` itself return the
+    complete G with one PCIe round trip; kept for hosts that want torch to own the all-reduce.)
+    G build for HOST matrices on `world` ranks with ONE PCIe round trip per call: D goes pinned host -> device,
     `fock_build_g_device` produces this rank's partial G, the partials are summed on the device (one NCCL
     all-reduce of N*N doubles) and only the sum returns to the host.  (`fock_build_g` + `allreduce_host_matrix`
     would move G down, up again for NCCL and down once more.)  D must be symmetric, as the reference's density
@@ -78,12 +80,16 @@ class HostStagedG:
 
         self.b = builder
         n = builder.n
-        self.stream = stream if stream is not None else torch.cuda.Stream()  # never the legacy default stream
         self.Dp = torch.empty((n, n), dtype=torch.float64).pin_memory()
         self.Gp = torch.empty((n, n), dtype=torch.float64).pin_memory()
+        # on the BUILDER's device (fock_opts.device; -1 = the CUDA runtime's current device at fock_create), not torch's current one
+        ordinal = int(builder.opts.device)
+        dev = torch.device("cuda", ordinal if ordinal >= 0 else torch.cuda.current_device())
+        with torch.cuda.device(dev):
+            self.stream = stream if stream is not None else torch.cuda.Stream(device=dev)
         with torch.cuda.stream(self.stream):
-            self.D = torch.empty((n, n), dtype=torch.float64, device="cuda")
-            self.G = torch.empty((n, n), dtype=torch.float64, device="cuda")
+            self.D = torch.empty((n, n), dtype=torch.float64, device=dev)
+            self.G = torch.empty((n, n), dtype=torch.float64, device=dev)
         self.stream.synchronize()
 
     def __call__(self, D_host) -> np.ndarray:
