@@ -372,7 +372,7 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
                     launch_work += q * sb.K * sk.K * kCost[cb][ck];
                 }
             }
-            const double loop_limit = std::max(6000.0, 0.25 * launch_work / ((double)num_sms * 8 * kClassThreads));
+            const double loop_limit = std::max(6000.0, 0.25 * launch_work / ((double)num_sms * 8 * 128));
             for (int b = 0; b < ns; ++b) {
                 const Sublist &sb = sd->sublists[b];
                 if (sb.cls != cb || sb.pair_ids.empty()) continue;
