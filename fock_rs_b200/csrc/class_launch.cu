@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <numeric>
 
+#include <cub/device/device_scan.cuh>
 #include <cub/device/device_segmented_sort.cuh>
 
 #include "../../include/fock_b200.h"
@@ -62,7 +63,7 @@ void launch_diag_mode(const DiagLaunch &dl, const DiagSink &sink, int mode, dim3
 // One launch for all sublists; block = one pair.
 __global__ void permute_pairs_kernel(const PermuteDesc *__restrict__ descs, int count, const double *__restrict__ bra_nat, const int *__restrict__ meta_nat,
                                      const int *__restrict__ perm, double *__restrict__ bra, double *__restrict__ ket,
-                                     int *__restrict__ meta) {
+                                     int *__restrict__ meta, const unsigned long long *__restrict__ maxdiag_nat, double *__restrict__ md_sorted) {
     const int g = blockIdx.x;
     int s = 0, hi = count - 1;  // largest s with descs[s].first <= g
     while (s < hi) {
@@ -82,6 +83,7 @@ __global__ void permute_pairs_kernel(const PermuteDesc *__restrict__ descs, int 
         ok[(size_t)e * d.npad] = v;  // e = ij*nf + f
     }
     if (threadIdx.x < 2) meta[d.meta_off + 2 * i + threadIdx.x] = meta_nat[d.meta_off + 2 * src + threadIdx.x];
+    if (threadIdx.x == 2) md_sorted[d.meta_off / 2 + i] = __longlong_as_double((long long)maxdiag_nat[d.meta_off / 2 + src]);
 }
 
 // per-pair max |(xy|xy)| of the pairs [first, first+n) of the natural-order meta table, from the
@@ -102,6 +104,107 @@ __global__ void class_pairmax_kernel(const int *__restrict__ meta_nat, const int
     maxdiag[first + i] = (unsigned long long)__double_as_longlong(m);
 }
 
+// sort key of the spatial order: magnitude bucket of the pair's largest diagonal integral (strong first) above the
+// Morton code of the pair centre
+__global__ void spatial_keys_kernel(const unsigned long long *__restrict__ maxdiag, const unsigned long long *__restrict__ morton, int n,
+                                    int bucket_bits, unsigned long long *__restrict__ keys) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int e = (int)(maxdiag[i] >> 52) & 0x7ff;  // biased exponent of a non-negative double (inf / NaN-as-inf: 2047 -> bucket 0)
+    const int b = min(255, max(0, 1030 - e) >> bucket_bits);
+    keys[i] = ((unsigned long long)b << 48) | (morton[i] & 0xffffffffffffULL);
+}
+
+// ---- CSR of the surviving quartets (spatial pair order) ---------------------------------------------------------------
+// One candidate job = (bra sublist, ket sublist) of a class pair.  Its rows are numbered plan-wide from `row_base`; a quartet
+// (r, c) survives when the shell-level bound on the per-pair maxima passes (pair_bound_passes below; the exact per-function
+// rule is re-applied in the sinks) and, inside one sublist, c <= r.
+struct PlanJobDesc {
+    long long row_base;
+    int md_b, md_k;  // first pair of the bra / ket sublist in the sorted per-pair maxima
+    int nb, nk;
+    int same, pad;
+};
+
+__device__ __forceinline__ int plan_job_of_row(const PlanJobDesc *__restrict__ jobs, int njobs, long long w) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].row_base <= w) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// pass 1: survivors per row (one warp per row)
+__global__ void plan_count_kernel(const PlanJobDesc *__restrict__ jobs, int njobs, long long total_rows, const double *__restrict__ md,
+                                  double thr2, long long *__restrict__ cnt, long long *__restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total_rows; w += nwarps) {
+        const PlanJobDesc j = jobs[plan_job_of_row(jobs, njobs, w)];
+        const int r = (int)(w - j.row_base);
+        const double db = md[j.md_b + r];
+        const int limit = j.same ? r + 1 : j.nk;
+        int n = 0;
+        for (int c0 = 0; c0 < limit; c0 += 32) {
+            const int c = c0 + lane;
+            const bool ok = c < limit && db * md[j.md_k + c] > thr2;
+            n += __popc(__ballot_sync(0xffffffffu, ok));
+        }
+        if (lane == 0) {
+            cnt[w] = n;
+            flag[w] = n > 0;
+        }
+    }
+}
+
+// pass 2 (after the two scans): list the non-empty rows -- their quartet offset and bra pair
+__global__ void plan_compact_kernel(const PlanJobDesc *__restrict__ jobs, int njobs, long long total_rows, const long long *__restrict__ cnt,
+                                    const long long *__restrict__ gprefix, const long long *__restrict__ cflag,
+                                    long long *__restrict__ cprefix, int *__restrict__ crow) {
+    for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w <= total_rows; w += (long long)gridDim.x * blockDim.x) {
+        if (w == total_rows) {
+            cprefix[cflag[w]] = gprefix[w];  // sentinel: one past the last listed row
+        } else if (cnt[w] > 0) {
+            const PlanJobDesc j = jobs[plan_job_of_row(jobs, njobs, w)];
+            cprefix[cflag[w]] = gprefix[w];
+            crow[cflag[w]] = (int)(w - j.row_base);
+        }
+    }
+}
+
+// pass 3: the ket pair of every surviving quartet, in row order (one warp per row)
+__global__ void plan_fill_kernel(const PlanJobDesc *__restrict__ jobs, int njobs, long long total_rows, const double *__restrict__ md,
+                                 double thr2, const long long *__restrict__ gprefix, int *__restrict__ col) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < total_rows; w += nwarps) {
+        if (gprefix[w + 1] == gprefix[w]) continue;
+        const PlanJobDesc j = jobs[plan_job_of_row(jobs, njobs, w)];
+        const int r = (int)(w - j.row_base);
+        const double db = md[j.md_b + r];
+        const int limit = j.same ? r + 1 : j.nk;
+        long long out = gprefix[w];
+        for (int c0 = 0; c0 < limit; c0 += 32) {
+            const int c = c0 + lane;
+            const bool ok = c < limit && db * md[j.md_k + c] > thr2;
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) col[out + __popc(m & ((1u << lane) - 1u))] = c;
+            out += __popc(m);
+        }
+    }
+}
+
+// quartet / listed-row offsets at the start of every candidate job (+ the totals)
+__global__ void plan_jobsum_kernel(const PlanJobDesc *__restrict__ jobs, int njobs, long long total_rows, const long long *__restrict__ gprefix,
+                                   const long long *__restrict__ cflag, long long *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > njobs) return;
+    const long long w = j < njobs ? jobs[j].row_base : total_rows;
+    out[2 * j] = gprefix[w];
+    out[2 * j + 1] = cflag[w];
+}
+
 // (job, first row) of every warp tile of a class launch: what the kernel would otherwise search for per tile
 // (two dependent ballot rounds over the job table, three over the row prefixes); one thread per tile, once per plan.
 __global__ void tile_table_kernel(const ClassJob *__restrict__ jobs, int njobs, long long total_tiles, int2 *__restrict__ out) {
@@ -112,7 +215,7 @@ __global__ void tile_table_kernel(const ClassJob *__restrict__ jobs, int njobs, 
             if (jobs[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
         }
         const long long *prefix = jobs[lo].row_prefix;
-        const long long q0 = (t - jobs[lo].tile_begin) * (32 / jobs[lo].ksplit);
+        const long long q0 = (t - jobs[lo].tile_begin) * (32 / jobs[lo].ksplit) + jobs[lo].q_base;
         int a = 0, b = jobs[lo].nb - 1;
         while (a < b) {  // largest row with prefix[row] <= q0 (skips empty rows, like warp_search)
             const int mid = (a + b + 1) >> 1;
@@ -141,9 +244,64 @@ int ClassEngine::upload_master(std::string &err) {
         (e = alloc((void **)&d_keys_sorted, meta.size() * 4 + 8)) != cudaSuccess ||
         (e = cudaMallocHost((void **)&h_keys_sorted, meta.size() * 4 + 8)) != cudaSuccess ||
         (e = alloc((void **)&d_iota, meta.size() * 2 + 8)) != cudaSuccess ||
-        (e = alloc((void **)&d_seg, (2 * sd->sublists.size() + 2) * sizeof(int))) != cudaSuccess) {
+        (e = alloc((void **)&d_seg, (2 * sd->sublists.size() + 2) * sizeof(int))) != cudaSuccess ||
+        (e = alloc((void **)&d_md_sorted, meta.size() * 4 + 8)) != cudaSuccess || (e = alloc((void **)&d_morton, meta.size() * 4 + 8)) != cudaSuccess ||
+        (e = alloc((void **)&d_sortkeys, meta.size() * 4 + 8)) != cudaSuccess) {
         err = std::string("pair tables: ") + cudaGetErrorString(e);
         return 1;
+    }
+    {
+        const char *po = getenv("FOCK_PAIR_ORDER");
+        spatial_order = !(po && std::string(po) == "diag");
+        // static sort keys of the spatial order: 3 x 16-bit Morton code of the pair centre (the product centre of the two most
+        // diffuse primitives: the primitive pairs that decide near / far field), natural order of every sublist
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (const Shell &sh : sd->shells)
+            for (int d = 0; d < 3; ++d) {
+                lo[d] = std::min(lo[d], sh.c[d]);
+                hi[d] = std::max(hi[d], sh.c[d]);
+            }
+        double ext = 1e-9;
+        for (int d = 0; d < 3; ++d) ext = std::max(ext, hi[d] - lo[d]);
+        auto min_exp = [&](const Shell &sh) {
+            double m = sd->exps[sh.prim_begin];
+            for (int i = 1; i < sh.nprim; ++i) m = std::min(m, sd->exps[sh.prim_begin + i]);
+            return m;
+        };
+        auto spread = [](unsigned long long v) {  // 16 bits -> every third bit
+            unsigned long long r = 0;
+            for (int i = 0; i < 16; ++i) r |= ((v >> i) & 1ULL) << (3 * i);
+            return r;
+        };
+        std::vector<unsigned long long> keys(meta.size() / 2 + 1, 0ULL);
+        for (const Sublist &sl : sd->sublists)
+            for (size_t i = 0; i < sl.pair_ids.size(); ++i) {
+                const ShellPair &pr = sd->pairs[sl.pair_ids[i]];
+                const Shell &A = sd->shells[pr.A], &B = sd->shells[pr.B];
+                const double a = min_exp(A), b = min_exp(B);
+                unsigned long long key = 0;
+                for (int d = 0; d < 3; ++d) {
+                    const double c = (a * A.c[d] + b * B.c[d]) / (a + b);
+                    const double t = std::min(1.0, std::max(0.0, (c - lo[d]) / ext));
+                    key |= spread((unsigned long long)(t * 65535.0)) << d;
+                }
+                keys[sl.meta_off / 2 + i] = key;
+            }
+        if (const char *bb = getenv("FOCK_ORDER_BUCKET_BITS")) order_bucket_bits = std::max(0, std::min(10, atoi(bb)));
+        cudaMemcpy(d_morton, keys.data(), (meta.size() / 2) * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+        // pure Morton order is static, so it is fixed here, on the host, with a stable sort: every rank of a multi-GPU run must
+        // number the pairs identically (ranks take interleaved warp tiles of the same plan)
+        if (spatial_order && order_bucket_bits == 0) {
+            std::vector<int> perm(meta.size() / 2 + 1, 0), idx;
+            for (const Sublist &sl : sd->sublists) {
+                const size_t base = sl.meta_off / 2, n = sl.pair_ids.size();
+                idx.resize(n);
+                std::iota(idx.begin(), idx.end(), 0);
+                std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return keys[base + x] < keys[base + y]; });
+                for (size_t i = 0; i < n; ++i) perm[base + i] = idx[i];
+            }
+            cudaMemcpy(d_perm, perm.data(), (meta.size() / 2) * sizeof(int), cudaMemcpyHostToDevice);
+        }
     }
     std::vector<int> sbf(sd->shells.size() * 6);
     for (size_t s = 0; s < sd->shells.size(); ++s)
@@ -199,11 +357,15 @@ int ClassEngine::upload_master(std::string &err) {
         cudaMemcpy(d_seg, seg.data(), seg.size() * sizeof(int), cudaMemcpyHostToDevice);
         sort_temp_bytes = 0;
         cudaGetLastError();  // the size query reports any error left pending on this thread as its own
+        size_t bytes_stable = 0;
         if ((e = cub::DeviceSegmentedSort::SortPairsDescending(nullptr, sort_temp_bytes, d_maxdiag, d_keys_sorted, d_iota, d_perm, npairs, nseg,
-                                                               d_seg, d_seg + nseg, stream)) != cudaSuccess) {
+                                                               d_seg, d_seg + nseg, stream)) != cudaSuccess ||
+            (e = cub::DeviceSegmentedSort::StableSortPairs(nullptr, bytes_stable, d_sortkeys, d_keys_sorted, d_iota, d_perm, npairs, nseg, d_seg,
+                                                           d_seg + nseg, stream)) != cudaSuccess) {
             err = std::string("sort scratch query: ") + cudaGetErrorString(e);
             return 1;
         }
+        sort_temp_bytes = std::max(sort_temp_bytes, bytes_stable);
         if ((e = cudaMalloc(&d_sort_temp, sort_temp_bytes + 16)) != cudaSuccess) {
             err = std::string("sort scratch: ") + cudaGetErrorString(e);
             return 1;
@@ -264,16 +426,27 @@ int ClassEngine::finish_diagonal(const double *d_diag, std::string &err) {
     // like their bit patterns -- and permute the primitive-pair tables accordingly; the host only needs
     // the sorted maxima (for the screening prefixes) and, for the shell-quartet path, the natural ones
     const int nseg = (int)sd->sublists.size();
-    if (cudaError_t se = cub::DeviceSegmentedSort::SortPairsDescending(d_sort_temp, sort_temp_bytes, d_maxdiag, d_keys_sorted, d_iota, d_perm,
-                                                                       (int)npairs, nseg, d_seg, d_seg + nseg, stream); se != cudaSuccess) {
-        err = std::string("diagonal sort: ") + cudaGetErrorString(se);
+    // spatial order: (magnitude bucket, Morton code) keys, stable sort (ties keep the natural order, so every rank of a
+    // multi-GPU run numbers the pairs identically); pure Morton order was fixed at upload
+    cudaError_t se = cudaSuccess;
+    if (!spatial_order) {
+        se = cub::DeviceSegmentedSort::SortPairsDescending(d_sort_temp, sort_temp_bytes, d_maxdiag, d_keys_sorted, d_iota, d_perm, (int)npairs, nseg,
+                                                           d_seg, d_seg + nseg, stream);
+    } else if (order_bucket_bits > 0) {
+        spatial_keys_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, stream>>>(d_maxdiag, d_morton, (int)npairs, order_bucket_bits, d_sortkeys);
+        se = cub::DeviceSegmentedSort::StableSortPairs(d_sort_temp, sort_temp_bytes, d_sortkeys, d_keys_sorted, d_iota, d_perm, (int)npairs, nseg,
+                                                       d_seg, d_seg + nseg, stream);
+        launches += 1;
+    }
+    if (se != cudaSuccess) {
+        err = std::string("sublist sort: ") + cudaGetErrorString(se);
         return -1;
     }
     if (permute_blocks > 0)
         permute_pairs_kernel<<<permute_blocks, 64, 0, stream>>>(d_permute_desc, permute_count, d_bra_nat, d_meta_nat, d_perm, dev->d_bra, dev->d_ket,
-                                                               dev->d_meta);
+                                                               dev->d_meta, d_maxdiag, d_md_sorted);
     launches += 2;
-    cudaMemcpyAsync(h_keys_sorted, d_keys_sorted, npairs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
+    cudaMemcpyAsync(h_keys_sorted, d_md_sorted, npairs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);  // maxima in sorted order
     cudaMemcpyAsync(h_maxdiag, d_maxdiag, npairs * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -320,7 +493,10 @@ static int surviving_prefix(double db, const std::vector<double> &dk, int screen
 int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::string &err) {
     if (plan_valid && plan_screen == screen && plan_thr == thr && plan_rank == rank && plan_world == world) return 0;
     const int ns = (int)sd->sublists.size();
-    std::vector<std::vector<double>> md(ns);  // per sublist: maxima in sorted (descending) order
+    // screened plan in spatial order: the survivors are a CSR matrix built on the device; otherwise (no screening, or the r01
+    // order by largest diagonal integral) a dense staircase whose row lengths the host walks down
+    const bool csr = spatial_order && screen != FOCK_SCREEN_OFF;
+    std::vector<std::vector<double>> md(ns);  // per sublist: maxima in sorted order
     {
         const double *sorted = reinterpret_cast<const double *>(h_keys_sorted);
         for (int s = 0; s < ns; ++s) {
@@ -328,11 +504,124 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
             md[s].assign(sorted + base, sorted + base + n);
         }
     }
+    cudaError_t e;
+    // ---- CSR, phase 1: every candidate job (same nested order as the launch loop below) -> row counts, scans, column lists
+    std::vector<PlanJobDesc> cand;
+    std::vector<int> cand_of(csr ? (size_t)ns * ns : 0, -1);
+    if (csr) {
+        long long total_rows = 0;
+        for (int cb = 0; cb < kNumPairClasses; ++cb)
+            for (int ck = 0; ck <= cb; ++ck)
+                for (int b = 0; b < ns; ++b) {
+                    const Sublist &sb = sd->sublists[b];
+                    if (sb.cls != cb || sb.pair_ids.empty()) continue;
+                    for (int k = 0; k <= b; ++k) {
+                        const Sublist &sk = sd->sublists[k];
+                        if (sk.cls != ck || sk.pair_ids.empty()) continue;
+                        cand_of[(size_t)b * ns + k] = (int)cand.size();
+                        cand.push_back(PlanJobDesc{total_rows, (int)(sb.meta_off / 2), (int)(sk.meta_off / 2), (int)sb.pair_ids.size(),
+                                                   (int)sk.pair_ids.size(), b == k ? 1 : 0, 0});
+                        total_rows += (long long)sb.pair_ids.size();
+                    }
+                }
+        const int nc = (int)cand.size();
+        if (nc > 0) {
+            if ((size_t)nc + 2 > plan_desc_cap) {
+                if (d_plan_desc) cudaFree(d_plan_desc);
+                if (h_plan_desc) cudaFreeHost(h_plan_desc);
+                if (d_jobsum) cudaFree(d_jobsum);
+                if (h_jobsum) cudaFreeHost(h_jobsum);
+                d_plan_desc = h_plan_desc = nullptr;
+                d_jobsum = h_jobsum = nullptr;
+                plan_desc_cap = (size_t)nc + 64;
+                if ((e = cudaMalloc(&d_plan_desc, plan_desc_cap * sizeof(PlanJobDesc))) != cudaSuccess ||
+                    (e = cudaMallocHost(&h_plan_desc, plan_desc_cap * sizeof(PlanJobDesc))) != cudaSuccess ||
+                    (e = cudaMalloc((void **)&d_jobsum, plan_desc_cap * 2 * sizeof(long long))) != cudaSuccess ||
+                    (e = cudaMallocHost((void **)&h_jobsum, plan_desc_cap * 2 * sizeof(long long))) != cudaSuccess) {
+                    err = std::string("plan descriptors: ") + cudaGetErrorString(e);
+                    plan_desc_cap = 0;
+                    return 1;
+                }
+            }
+            if ((size_t)total_rows + 2 > rows_cap) {
+                for (void *q : {(void *)d_rowcnt, (void *)d_gprefix, (void *)d_rowflag, (void *)d_cflag, (void *)d_cprefix, (void *)d_crow, d_scan_temp})
+                    if (q) cudaFree(q);
+                d_rowcnt = d_gprefix = d_rowflag = d_cflag = d_cprefix = nullptr;
+                d_crow = nullptr;
+                d_scan_temp = nullptr;
+                rows_cap = (size_t)total_rows + (size_t)total_rows / 8 + 1024;
+                scan_temp_bytes = 0;
+                cudaGetLastError();
+                if ((e = cudaMalloc((void **)&d_rowcnt, rows_cap * sizeof(long long))) != cudaSuccess ||
+                    (e = cudaMalloc((void **)&d_gprefix, rows_cap * sizeof(long long))) != cudaSuccess ||
+                    (e = cudaMalloc((void **)&d_rowflag, rows_cap * sizeof(long long))) != cudaSuccess ||
+                    (e = cudaMalloc((void **)&d_cflag, rows_cap * sizeof(long long))) != cudaSuccess ||
+                    (e = cudaMalloc((void **)&d_cprefix, rows_cap * sizeof(long long))) != cudaSuccess ||
+                    (e = cudaMalloc((void **)&d_crow, rows_cap * sizeof(int))) != cudaSuccess ||
+                    (e = cub::DeviceScan::ExclusiveSum(nullptr, scan_temp_bytes, d_rowcnt, d_gprefix, (int)rows_cap, stream)) != cudaSuccess ||
+                    (e = cudaMalloc(&d_scan_temp, scan_temp_bytes + 16)) != cudaSuccess) {
+                    err = std::string("plan row tables: ") + cudaGetErrorString(e);
+                    rows_cap = 0;
+                    return 1;
+                }
+            }
+            std::copy(cand.begin(), cand.end(), reinterpret_cast<PlanJobDesc *>(h_plan_desc));
+            const PlanJobDesc *dj = reinterpret_cast<const PlanJobDesc *>(d_plan_desc);
+            const double thr2 = thr * thr * (1.0 - 1e-12);  // pair_bound_passes
+            cudaMemcpyAsync(d_plan_desc, h_plan_desc, (size_t)nc * sizeof(PlanJobDesc), cudaMemcpyHostToDevice, stream);
+            cudaMemsetAsync(d_rowcnt + total_rows, 0, sizeof(long long), stream);
+            cudaMemsetAsync(d_rowflag + total_rows, 0, sizeof(long long), stream);
+            const unsigned wblocks = (unsigned)std::min<long long>((total_rows + 7) / 8, (long long)num_sms * 32);
+            plan_count_kernel<<<wblocks, 256, 0, stream>>>(dj, nc, total_rows, d_md_sorted, thr2, d_rowcnt, d_rowflag);
+            size_t tb = scan_temp_bytes;
+            cub::DeviceScan::ExclusiveSum(d_scan_temp, tb, d_rowcnt, d_gprefix, (int)(total_rows + 1), stream);
+            tb = scan_temp_bytes;
+            cub::DeviceScan::ExclusiveSum(d_scan_temp, tb, d_rowflag, d_cflag, (int)(total_rows + 1), stream);
+            plan_jobsum_kernel<<<(nc + 1 + 127) / 128, 128, 0, stream>>>(dj, nc, total_rows, d_gprefix, d_cflag, d_jobsum);
+            cudaMemcpyAsync(h_jobsum, d_jobsum, (size_t)(nc + 1) * 2 * sizeof(long long), cudaMemcpyDeviceToHost, stream);
+            if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) {
+                err = std::string("plan row counts: ") + cudaGetErrorString(e);
+                return 1;
+            }
+            const long long total_q = h_jobsum[2 * nc];
+            if ((size_t)total_q + 1 > colidx_cap) {
+                if (d_colidx) cudaFree(d_colidx);
+                d_colidx = nullptr;
+                colidx_cap = (size_t)total_q + (size_t)total_q / 16 + 1024;
+                if ((e = cudaMalloc((void **)&d_colidx, colidx_cap * sizeof(int))) != cudaSuccess) {
+                    err = std::string("plan column lists (") + std::to_string(colidx_cap * sizeof(int) >> 20) + " MiB): " + cudaGetErrorString(e);
+                    colidx_cap = 0;
+                    return 1;
+                }
+            }
+            plan_compact_kernel<<<(unsigned)std::min<long long>((total_rows + 256) / 256, (long long)num_sms * 32), 256, 0, stream>>>(
+                dj, nc, total_rows, d_rowcnt, d_gprefix, d_cflag, d_cprefix, d_crow);
+            plan_fill_kernel<<<wblocks, 256, 0, stream>>>(dj, nc, total_rows, d_md_sorted, thr2, d_gprefix, d_colidx);
+        }
+    }
     std::vector<long long> table;
     std::vector<ClassJob> jobs;
     std::vector<size_t> job_table_off;
     plan.clear();
     plan_stats = ClassStats();
+    // quartets of the (b, k) job: exact (CSR) or estimated from 64 sampled rows (staircase)
+    auto job_quartets_estimate = [&](int b, int k) -> double {
+        const int nb = (int)sd->sublists[b].pair_ids.size(), nk = (int)sd->sublists[k].pair_ids.size();
+        if (csr) {
+            const int ci = cand_of[(size_t)b * ns + k];
+            return (double)(h_jobsum[2 * (ci + 1)] - h_jobsum[2 * ci]);
+        }
+        if (screen == FOCK_SCREEN_OFF) return (b == k) ? 0.5 * nb * (nb + 1.0) : (double)nb * nk;
+        const int step = std::max(1, nb / 64);
+        int cnt = 0;
+        double q = 0.0;
+        for (int r = 0; r < nb; r += step, ++cnt) {
+            int nc = surviving_prefix(md[b][r], md[k], screen, thr);
+            if (b == k) nc = std::min(nc, r + 1);
+            q += nc;
+        }
+        return q * (double)nb / std::max(cnt, 1);
+    };
     // class pairs in a fixed order; within one, every (bra sublist >= ket sublist) job
     for (int cb = 0; cb < kNumPairClasses; ++cb)
         for (int ck = 0; ck <= cb; ++ck) {
@@ -355,21 +644,7 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
                 for (int k = 0; k <= b; ++k) {
                     const Sublist &sk = sd->sublists[k];
                     if (sk.cls != ck || sk.pair_ids.empty()) continue;
-                    const int nb = (int)sb.pair_ids.size(), nk = (int)sk.pair_ids.size();
-                    double q = 0.0;
-                    if (screen == FOCK_SCREEN_OFF) {
-                        q = (b == k) ? 0.5 * nb * (nb + 1.0) : (double)nb * nk;
-                    } else {  // cheap estimate: sample 64 rows
-                        const int step = std::max(1, nb / 64);
-                        int cnt = 0;
-                        for (int r = 0; r < nb; r += step, ++cnt) {
-                            int nc = surviving_prefix(md[b][r], md[k], screen, thr);
-                            if (b == k) nc = std::min(nc, r + 1);
-                            q += nc;
-                        }
-                        q *= (double)nb / std::max(cnt, 1);
-                    }
-                    launch_work += q * sb.K * sk.K * kCost[cb][ck];
+                    launch_work += job_quartets_estimate(b, k) * sb.K * sk.K * kCost[cb][ck];
                 }
             }
             const double loop_limit = std::max(6000.0, 0.25 * launch_work / ((double)num_sms * 8 * 128));
@@ -381,20 +656,27 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
                     if (sk.cls != ck || sk.pair_ids.empty()) continue;
                     const int nb = (int)sb.pair_ids.size(), nk = (int)sk.pair_ids.size();
                     const size_t off = table.size();
-                    table.resize(off + (size_t)nb + 1);
-                    long long *prefix = table.data() + off;
                     long long quartets = 0;
-                    const double *mdb = md[b].data(), *mdk = md[k].data();
-                    const double thr2_slack = thr * thr * (1.0 - 1e-12);
-                    // ncols(r) is non-increasing in r (both lists sorted descending): walk it down
-                    int nc = (screen == FOCK_SCREEN_OFF) ? nk : surviving_prefix(md[b][0], md[k], screen, thr);
-                    for (int r = 0; r < nb; ++r) {
-                        if (screen != FOCK_SCREEN_OFF)
-                            while (nc > 0 && !pair_bound_passes(mdb[r], mdk[nc - 1], thr2_slack)) --nc;
-                        prefix[r] = quartets;
-                        quartets += (b == k) ? std::min(nc, r + 1) : nc;
+                    int rows_listed = nb;
+                    const int ci = csr ? cand_of[(size_t)b * ns + k] : -1;
+                    if (csr) {
+                        quartets = h_jobsum[2 * (ci + 1)] - h_jobsum[2 * ci];
+                        rows_listed = (int)(h_jobsum[2 * (ci + 1) + 1] - h_jobsum[2 * ci + 1]);
+                    } else {
+                        table.resize(off + (size_t)nb + 1);
+                        long long *prefix = table.data() + off;
+                        const double *mdb = md[b].data(), *mdk = md[k].data();
+                        const double thr2_slack = thr * thr * (1.0 - 1e-12);
+                        // ncols(r) is non-increasing in r (both lists sorted descending): walk it down
+                        int nc = (screen == FOCK_SCREEN_OFF) ? nk : surviving_prefix(md[b][0], md[k], screen, thr);
+                        for (int r = 0; r < nb; ++r) {
+                            if (screen != FOCK_SCREEN_OFF)
+                                while (nc > 0 && !pair_bound_passes(mdb[r], mdk[nc - 1], thr2_slack)) --nc;
+                            prefix[r] = quartets;
+                            quartets += (b == k) ? std::min(nc, r + 1) : nc;
+                        }
+                        prefix[nb] = quartets;
                     }
-                    prefix[nb] = quartets;
                     // K-split: keep one thread's loop below ~6000 instructions (class cost x depth)
                     static const int kSplitMax = getenv("FOCK_KSPLIT_MAX") ? atoi(getenv("FOCK_KSPLIT_MAX")) : 32;
                     int S = 1;
@@ -419,10 +701,16 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
                     j.ket_meta = dev->d_meta + sk.meta_off;
                     j.Kab = sb.K;
                     j.Kcd = sk.K;
-                    j.nb = nb;
+                    j.nb = rows_listed;
                     j.nk_pad = sk.npad;
                     j.same_sublist = (b == k) ? 1 : 0;
                     j.ksplit = S;
+                    if (csr) {
+                        j.q_base = h_jobsum[2 * ci];
+                        j.row_prefix = d_cprefix + h_jobsum[2 * ci + 1];
+                        j.row_map = d_crow + h_jobsum[2 * ci + 1];
+                        j.col_idx = d_colidx + j.q_base;
+                    }
                     jobs.push_back(j);
                     job_table_off.push_back(off);
                     tiles_launch += tiles;
@@ -458,7 +746,6 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
             pl.total_tiles = tiles_launch;
             if (pl.njobs > 0) plan.push_back(pl);
         }
-    cudaError_t e;
     if (table.size() + 1 > table_cap) {
         if (d_table) cudaFree(d_table);
         if (h_table) cudaFreeHost(h_table);
@@ -485,7 +772,8 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
             return 1;
         }
     }
-    for (size_t i = 0; i < jobs.size(); ++i) jobs[i].row_prefix = d_table + job_table_off[i];
+    if (!csr)
+        for (size_t i = 0; i < jobs.size(); ++i) jobs[i].row_prefix = d_table + job_table_off[i];
     // pinned staging: the copies are truly asynchronous and ordered before the launches on `stream`
     std::copy(table.begin(), table.end(), h_table);
     std::copy(jobs.begin(), jobs.end(), h_jobs);
@@ -613,6 +901,11 @@ template int ClassEngine::run_plan<TensorSink>(const TensorSink &, std::string &
 template int ClassEngine::run_plan<BlockDirectSink>(const BlockDirectSink &, std::string &);
 
 ClassEngine::~ClassEngine() {
+    for (void *q : {(void *)d_md_sorted, (void *)d_morton, (void *)d_sortkeys, d_plan_desc, (void *)d_rowcnt, (void *)d_gprefix, (void *)d_rowflag, (void *)d_cflag,
+                    (void *)d_cprefix, (void *)d_crow, (void *)d_colidx, (void *)d_jobsum, d_scan_temp})
+        if (q) cudaFree(q);
+    if (h_plan_desc) cudaFreeHost(h_plan_desc);
+    if (h_jobsum) cudaFreeHost(h_jobsum);
     if (d_table) cudaFree(d_table);
     if (d_tile_tab) cudaFree(d_tile_tab);
     if (d_tile_counters) cudaFree(d_tile_counters);

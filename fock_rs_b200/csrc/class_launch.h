@@ -84,6 +84,31 @@ struct ClassEngine {
     double host_ms[4] = {0, 0, 0, 0};  // sort, plan
     ClassJob *d_jobs = nullptr;
     size_t jobs_cap = 0;
+    // Pair order of the sublists.  Spatial (default): Morton order of the pair centres, so that the 32 ket pairs of a warp tile
+    // lie close together and meet the near / far Boys branch together; the quartets that survive the cut are then a CSR matrix
+    // built on the device per plan (row counts -> scans -> column lists).  FOCK_PAIR_ORDER=diag restores the r01 order (sorted by
+    // the largest diagonal integral, survivors of a row are a prefix, no column lists).
+    bool spatial_order = true;
+    double *d_md_sorted = nullptr;           // per pair, sorted order: max |(xy|xy)|
+    // sort keys of the spatial order: (magnitude bucket of the pair's largest diagonal integral, Morton code of its centre).
+    // Pairs that never survive the cut sink to the end of their sublist and the survivors of a row are dense runs of whole
+    // buckets (coalesced ket loads) plus one partially surviving bucket; inside a bucket neighbours in the list are neighbours
+    // in space.  order_bucket_bits = log2 of the bucket width (FOCK_ORDER_BUCKET_BITS; 0 = pure Morton order, fixed at upload).
+    unsigned long long *d_morton = nullptr, *d_sortkeys = nullptr;  // per pair, natural order
+    int order_bucket_bits = 4;
+    void *d_plan_desc = nullptr;             // PlanJobDesc[candidates]
+    void *h_plan_desc = nullptr;
+    size_t plan_desc_cap = 0;
+    long long *d_rowcnt = nullptr, *d_gprefix = nullptr, *d_rowflag = nullptr, *d_cflag = nullptr;  // [rows + 1]
+    size_t rows_cap = 0;
+    long long *d_cprefix = nullptr;  // [non-empty rows + 1] quartet offset of every listed row
+    int *d_crow = nullptr;           // [non-empty rows] bra pair of every listed row
+    int *d_colidx = nullptr;         // [quartets] ket pair of every surviving quartet
+    size_t colidx_cap = 0;
+    long long *d_jobsum = nullptr, *h_jobsum = nullptr;  // [candidates + 1][2]: quartet / listed-row offsets at job starts
+    size_t jobsum_cap = 0;
+    void *d_scan_temp = nullptr;
+    size_t scan_temp_bytes = 0;
     unsigned long long *d_tile_counters = nullptr;  // [class pairs][kTileCounterSlots], zeroed at the start of every run_plan
     int2 *d_tile_tab = nullptr;  // (job, first row) per warp tile of every launch of the plan
     size_t tile_tab_cap = 0;

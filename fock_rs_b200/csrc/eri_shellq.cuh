@@ -265,13 +265,17 @@ __global__ void __launch_bounds__(kSqThreads) eri_class_warpq_kernel(ClassLaunch
         while (j + 1 < cl.njobs && cl.jobs[j + 1].tile_begin <= tile) ++j;
         const ClassJob job = cl.jobs[j];
         const long long q0 = (tile - job.tile_begin) * kWarpqTile;  // ksplit is 1 for these jobs
-        const long long total_q = job.row_prefix[job.nb];
-        int row = warp_search(job.row_prefix, job.nb, q0, lane);
+        const long long total_q = job_prefix(job, job.nb);
+        int row = warp_search(job.row_prefix, job.nb, q0 + job.q_base, lane);
         for (long long q = q0; q < q0 + kWarpqTile && q < total_q; ++q) {
-            while (row + 1 < job.nb && job.row_prefix[row + 1] <= q) ++row;
-            const int col = (int)(q - job.row_prefix[row]);
-            sq_eval_quartet(env, s_tab, sc, lane, job.bra_meta[2 * row], job.bra_meta[2 * row + 1], job.ket_meta[2 * col],
-                            job.ket_meta[2 * col + 1], job.same_sublist && row == col, sink);
+            while (row + 1 < job.nb && job_prefix(job, row + 1) <= q) ++row;
+            int brow = row, kcol = (int)(q - job_prefix(job, row));
+            if (job.col_idx) {  // screened plan in spatial order: CSR of the surviving quartets (eri_class.cuh: ClassJob)
+                kcol = job.col_idx[q];
+                brow = job.row_map[row];
+            }
+            sq_eval_quartet(env, s_tab, sc, lane, job.bra_meta[2 * brow], job.bra_meta[2 * brow + 1], job.ket_meta[2 * kcol],
+                            job.ket_meta[2 * kcol + 1], job.same_sublist && brow == kcol, sink);
         }
     }
 }
