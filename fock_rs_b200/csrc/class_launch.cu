@@ -21,7 +21,7 @@ namespace {
 template <int LA, int LB, int LC, int LD, int KC0, int KCN, class Sink>
 void launch_mode(const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, cudaStream_t st) {
     constexpr int NAB = ncart_c(LA) * ncart_c(LB);
-    const size_t smem = boys_smem_bytes(LA + LB + LC + LD, cl.boys_ni);
+    const size_t smem = class_smem_bytes(LA, LB, LA + LB + LC + LD, cl.boys_ni);
     if (mode & FOCK_MODE_FIX_R_BIT)
         eri_class_kernel<LA, LB, LC, LD, 1, 0, NAB, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
     else

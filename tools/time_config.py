@@ -22,7 +22,10 @@ def main():
     mol, basis, screen, storage = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
     fb = flat_for(mol, basis)
     D = random_symmetric_density(fb.n_basis)
-    with FockBuilder(fb, screen=screen, storage=storage, keep_eri=False) as b:
+    # RANK / WORLD emulate one rank's share of a multi-GPU run on a single GPU (the tiles are dealt round-robin inside the kernels;
+    # G is then a partial sum): per-rank kernel time against the 1-GPU time / WORLD = what the tails and fixed costs take
+    rank, world = int(os.environ.get("RANK_EMU", "0")), int(os.environ.get("WORLD_EMU", "1"))
+    with FockBuilder(fb, screen=screen, storage=storage, keep_eri=False, rank=rank, world=world) as b:
         b.eri_build()
         b.build_g(D)  # warm-up
         t0 = time.time()
@@ -40,7 +43,7 @@ def main():
             reps.append(t["class_kernels_ms"])
         reps.sort()
     tflops = st["model_flops"] / (tm["class_kernels_ms"] * 1e-3) * 1e-12 if tm["class_kernels_ms"] > 0 else 0.0
-    print(os.environ.get("TAG", ""), mol, "screen", screen, "storage", storage,
+    print(os.environ.get("TAG", ""), ("rank %d/%d" % (rank, world)) if world > 1 else "", mol, "screen", screen, "storage", storage,
           "build %.2f ms g %.2f ms | class %.3f (min %.3f med %.3f of %d) g_dev %.3f sort %.2f plan %.2f tiles %d TF %.2f"
           % (1e3 * (t1 - t0), 1e3 * (t2 - t1), tm["class_kernels_ms"], reps[0] if reps else 0.0, reps[len(reps) // 2] if reps else 0.0, len(reps), tm["g_device_ms"], tm["host_sort_ms"], tm["host_plan_ms"],
              st["warp_tiles"], tflops), flush=True)
