@@ -22,6 +22,7 @@ template <int LA, int LB, int LC, int LD, int KC0, int KCN, class Sink>
 void launch_mode(const ClassLaunch &cl, const Sink &sink, int mode, dim3 grid, cudaStream_t st) {
     constexpr int NAB = ncart_c(LA) * ncart_c(LB);
     const size_t smem = class_smem_bytes(LA, LB, LA + LB + LC + LD, cl.boys_ni);
+    if (cl.ring) st = cl.ring->next();
     if (mode & FOCK_MODE_FIX_R_BIT)
         eri_class_kernel<LA, LB, LC, LD, 1, 0, NAB, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
     else
@@ -647,6 +648,7 @@ int ClassEngine::make_plan(int screen, double thr, int rank, int world, std::str
                     launch_work += job_quartets_estimate(b, k) * sb.K * sk.K * kCost[cb][ck];
                 }
             }
+            // (scaling the limit with 1/world was measured on an emulated 1/8 share: more K-split tiles, 8.9 -> 11.0 ms on config 5 -- not done)
             const double loop_limit = std::max(6000.0, 0.25 * launch_work / ((double)num_sms * 8 * 128));
             for (int b = 0; b < ns; ++b) {
                 const Sublist &sb = sd->sublists[b];
@@ -834,9 +836,14 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
     cudaEventRecord(ev_fork, stream);
     for (int i = 0; i < kAuxStreams; ++i) cudaStreamWaitEvent(aux[i], ev_fork, 0);
     int slot = 0;
+    StreamRing ring;
+    ring.n = kStreams;
+    for (int i = 0; i < kStreams; ++i) ring.s[i] = aux[i];
+    static const bool kSpreadSlices = !getenv("FOCK_NO_SLICE_SPREAD");
     for (int pi = (int)plan.size() - 1; pi >= 0; --pi) {  // plan is ordered light -> heavy
         const ClassPlanLaunch &pl = plan[pi];
         ClassLaunch cl{};
+        cl.ring = kSpreadSlices ? &ring : nullptr;
         cl.jobs = d_jobs + pl.job_begin;
         cl.njobs = pl.njobs;
         cl.total_tiles = pl.total_tiles;

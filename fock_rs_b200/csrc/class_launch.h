@@ -118,7 +118,7 @@ struct ClassEngine {
     int plan_screen = -1, plan_rank = -1, plan_world = -1;
     double plan_thr = 0;
 
-    static constexpr int kAuxStreams = 4;
+    static constexpr int kAuxStreams = 16;
     cudaStream_t aux[kAuxStreams] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kAuxStreams] = {};
 

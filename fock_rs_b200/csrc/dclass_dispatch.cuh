@@ -18,7 +18,7 @@ template <int LA, int LB, int LC, int LD, int CB0, int CBN, int KC0, int KCN, cl
 inline void launch_slice(const ClassLaunch &cl, const Sink &sink, dim3 grid, cudaStream_t st) {
     const size_t smem = class_smem_bytes(LA, LB, LA + LB + LC + LD, cl.boys_ni);
     // FIXR = 2: the (t-1) factor of the R recursion is a run-time flag here (halves the instantiations)
-    eri_class_kernel<LA, LB, LC, LD, 2, CB0, CBN, KC0, KCN, Sink><<<grid, kClassThreads, smem, st>>>(cl, sink);
+    eri_class_kernel<LA, LB, LC, LD, 2, CB0, CBN, KC0, KCN, Sink><<<grid, kClassThreads, smem, cl.ring ? cl.ring->next() : st>>>(cl, sink);
 }
 
 // ket component slices [0, N) in steps of STEP, all bra components [CB0, CB0+CBN)
