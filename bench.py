@@ -414,10 +414,15 @@ def bench_config(env, args, workload, storage, mode, steps, warmup, clocks_for=N
             b.eri_build()
         b.build_g_device(D.data_ptr(), G.data_ptr())
 
+    # host-buffer path: the caller's D and G are page-locked matrices (fock_pinned_alloc), as the bench contract's e2e asks --
+    # fock_build_g copies them straight to / from the device
+    Dpin, Gpin = b.pinned_matrix(), b.pinned_matrix()
+    Dpin[...] = Dh
+
     def step_host():
         if not direct:
             b.eri_build()
-        return b.build_g(Dh)
+        return b.build_g(Dpin, out=Gpin)
 
     def timed(fn, k):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(k)]
@@ -448,7 +453,7 @@ def bench_config(env, args, workload, storage, mode, steps, warmup, clocks_for=N
     if sampler:
         sampler.__exit__()
         clocks_for.update(sampler.summary())
-    g_host = step_host()
+    g_host = step_host().copy()
     t_dev_ms, t_host_ms = env.max_over_ranks(t_dev_ms, t_host_ms)
     ms_step, ms_e2e = t_dev_ms / steps, t_host_ms / steps
     torch.cuda.synchronize()

@@ -27,6 +27,7 @@ EXPORTS = [
     "fock_supermatrix_device", "fock_set_digest_range", "fock_timings", "fock_stats", "fock_last_error", "fock_destroy",
     "fock_abi_version", "fock_measure_fp64_peak", "fock_boys_batch",
     "fock_orbital_eval", "fock_orbital_voxelize", "fock_orbital_stats",
+    "fock_pinned_alloc", "fock_pinned_free",
     "fock_diagonal_export", "fock_comm_unique_id", "fock_comm_init", "fock_comm_destroy", "fock_comm_attached", "fock_comm_last_error",
 ]
 COMM_ID_BYTES = 128
@@ -113,7 +114,9 @@ def load():
     L.fock_comm_destroy.argtypes = [vp]
     L.fock_comm_attached.argtypes = [vp]
     L.fock_comm_last_error.restype = C.c_char_p
-    if L.fock_abi_version() != 4:
-        raise ImportError(f"{LIB_PATH} implements ABI version {L.fock_abi_version()}, this package binds version 4: rebuild it")
+    L.fock_pinned_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.fock_pinned_free.argtypes = [vp]
+    if L.fock_abi_version() != 5:
+        raise ImportError(f"{LIB_PATH} implements ABI version {L.fock_abi_version()}, this package binds version 5: rebuild it")
     _lib = L
     return L

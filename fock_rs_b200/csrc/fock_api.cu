@@ -767,20 +767,46 @@ int fock_build_g(fock_ctx *ctx, const double *D, double *G) {
     FOCK_TRY(ensure_g_buffers(ctx));
     const size_t nn = (size_t)ctx->N * ctx->N;
     cudaStream_t st = ctx->stream;
-    std::memcpy(ctx->h_pinned, D, nn * sizeof(double));
+    // page-locked caller buffers (fock_pinned_alloc, cudaHostRegister, ...) are copied directly; pageable ones are staged
+    auto page_locked = [](const void *p) {
+        cudaPointerAttributes a;
+        if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool d_direct = page_locked(D), g_direct = page_locked(G);
+    if (!d_direct) std::memcpy(ctx->h_pinned, D, nn * sizeof(double));
     FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_C], st));
-    FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_D, ctx->h_pinned, nn * sizeof(double), cudaMemcpyHostToDevice, st));
+    FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_D, d_direct ? D : ctx->h_pinned, nn * sizeof(double), cudaMemcpyHostToDevice, st));
     FOCK_TRY(fock_build_g_device(ctx, ctx->d_D, ctx->d_G));
-    FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_pinned + nn, ctx->d_G, nn * sizeof(double), cudaMemcpyDeviceToHost, st));
+    FOCK_CUDA_TRY(ctx, cudaMemcpyAsync(g_direct ? G : ctx->h_pinned + nn, ctx->d_G, nn * sizeof(double), cudaMemcpyDeviceToHost, st));
     FOCK_CUDA_TRY(ctx, cudaEventRecord(ctx->ev[EV_D], st));
     FOCK_CUDA_TRY(ctx, cudaStreamSynchronize(st));
-    std::memcpy(G, ctx->h_pinned + nn, nn * sizeof(double));
+    if (!g_direct) std::memcpy(G, ctx->h_pinned + nn, nn * sizeof(double));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[EV_E], ctx->ev[EV_F]);
     ctx->timings[3] = ms;
     cudaEventElapsedTime(&ms, ctx->ev[EV_C], ctx->ev[EV_D]);
     ctx->timings[4] = ms;
     return FOCK_OK;
+}
+
+int fock_pinned_alloc(size_t bytes, void **out) {
+    if (!out) return FOCK_ERR_BAD_ARG;
+    *out = nullptr;
+    const cudaError_t e = cudaMallocHost(out, bytes ? bytes : 8);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return e == cudaErrorMemoryAllocation ? FOCK_ERR_OOM : FOCK_ERR_CUDA;
+    }
+    return FOCK_OK;
+}
+
+int fock_pinned_free(void *p) {
+    if (!p) return FOCK_OK;
+    return cudaFreeHost(p) == cudaSuccess ? FOCK_OK : FOCK_ERR_CUDA;
 }
 
 int fock_one_electron(fock_ctx *ctx, int32_t n_nuc, const double *pos, const double *chg, double *S, double *T, double *V) {

@@ -39,6 +39,7 @@ class FockBuilder:
                  device=-1, rank=0, world=1, keep_eri=True, kernel=0, incore_shard=0, deterministic=False):
         self._L = _lib.load()
         self._ctx = C.c_void_p()
+        self._pinned = []  # page-locked matrices handed out by pinned_matrix(); they die with the builder
         flat = _as_flat(basis)
         self.flat = flat
         self.n = flat.n_basis
@@ -72,6 +73,9 @@ class FockBuilder:
         if getattr(self, "_ctx", None) and self._ctx.value:
             self._L.fock_destroy(self._ctx)
             self._ctx = C.c_void_p()
+        for p in getattr(self, "_pinned", []):
+            self._L.fock_pinned_free(p)
+        self._pinned = []
 
     def __del__(self):
         try:
@@ -149,14 +153,29 @@ class FockBuilder:
         self._check(self._L.fock_boys_batch(self._ctx, _dp(tt), tt.size, int(order), _dp(out)))
         return out
 
-    def build_g(self, D) -> np.ndarray:
-        """G = J - K/2 for a symmetric density (host buffers, column-major like DMatrix)."""
+    def build_g(self, D, out=None) -> np.ndarray:
+        """G = J - K/2 for a symmetric density (host buffers, column-major like DMatrix).  `out`: an N x N column-major float64
+        array to receive G; with `D` and `out` from `pinned_matrix()` the call copies straight between them and the device."""
         Dc = np.asfortranarray(D, dtype=np.float64)
         if Dc.shape != (self.n, self.n):
             raise ValueError("density must be N x N")
-        G = np.empty((self.n, self.n), dtype=np.float64, order="F")
+        if out is None:
+            G = np.empty((self.n, self.n), dtype=np.float64, order="F")
+        else:
+            G = out
+            if G.shape != (self.n, self.n) or G.dtype != np.float64 or not G.flags.f_contiguous:
+                raise ValueError("out must be an N x N column-major float64 array")
         self._check(self._L.fock_build_g(self._ctx, _dp(Dc), _dp(G)))
         return G
+
+    def pinned_matrix(self) -> np.ndarray:
+        """An N x N column-major float64 matrix in page-locked host memory (fock_pinned_alloc), freed with the builder."""
+        p = C.c_void_p()
+        nbytes = 8 * self.n * self.n
+        self._check(self._L.fock_pinned_alloc(nbytes, C.byref(p)))
+        self._pinned.append(p)
+        buf = (C.c_double * (self.n * self.n)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.float64).reshape((self.n, self.n), order="F")
 
     def build_g_device(self, d_ptr: int, g_ptr: int):
         """Device-resident D and G (raw device pointers, N*N doubles each, column-major)."""

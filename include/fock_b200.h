@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FOCK_B200_ABI_VERSION 4
+#define FOCK_B200_ABI_VERSION 5
 
 typedef struct fock_ctx fock_ctx;
 
@@ -137,6 +137,14 @@ int fock_diagonal_export(fock_ctx *ctx, double *host, size_t n);
  * one NCCL all-reduce of N*N doubles on the context's stream, inside this call; without a communicator it is
  * this rank's PARTIAL G and the caller sums the partials. */
 int fock_build_g(fock_ctx *ctx, const double *D, double *G);
+
+/* Page-locked host matrices for fock_build_g (ABI v5).  When D and/or G lie in page-locked memory (these, or any buffer the host
+ * registered with the CUDA runtime), fock_build_g copies straight between them and the device; pageable buffers go through the
+ * context's own staging area, one extra host copy each way (about 1 ms per 5 MB matrix).  The reference's DMatrix owns its
+ * storage (nalgebra, scf/src/lib.rs:95-96), so a binding keeps one such pair per SCF run and maps/copies the matrix views onto
+ * it.  Free with fock_pinned_free; the buffers are not tied to a context. */
+int fock_pinned_alloc(size_t bytes, void **out);
+int fock_pinned_free(void *p);
 
 /* Same with device-resident D and G (N*N doubles each) on the context's stream. */
 int fock_build_g_device(fock_ctx *ctx, const double *D_dev, double *G_dev);

@@ -13,6 +13,12 @@ from helpers import flat_for, random_symmetric_density
 pytestmark = pytest.mark.gpu
 
 
+def oracle_g(fb, D):
+    """The CPU oracle's G (faithful arithmetic, reference cut) for the flat basis fb."""
+    want, _ = oracle.direct_g(oracle.OracleBasis.from_flat(fb), D, oracle.FAITHFUL)
+    return want
+
+
 @pytest.mark.parametrize("storage", [_lib.STORAGE_INCORE, _lib.STORAGE_DIRECT], ids=["incore", "direct"])
 def test_schwarz_tau_1e6_is_the_reference_cut(storage):
     """FOCK_SCREEN_SCHWARZ applies the reference's own estimate sqrt((ij|ij)(kl|kl)) > tau
@@ -144,3 +150,47 @@ def test_d_shells_are_never_fragmented():
     for mol, basis in (("water", "6-31G**"), ("w4", "6-31G**"), ("water", "cc-pVDZ")):
         with FockBuilder(flat_for(mol, basis)) as b:
             assert b.stats()["partial_shells"] == 0
+
+
+@pytest.mark.parametrize("storage", [_lib.STORAGE_INCORE, _lib.STORAGE_DIRECT], ids=["incore", "direct"])
+def test_page_locked_matrices_take_the_same_path(storage):
+    """fock_build_g with D and G in page-locked memory (fock_pinned_alloc, ABI v5) copies straight to / from the device; the result
+    is the one the staged path gives for pageable buffers, and mixing the two kinds works."""
+    fb = flat_for("water_dimer", "6-31G")
+    D = random_symmetric_density(fb.n_basis, seed=5)
+    with FockBuilder(fb, storage=storage) as b:
+        b.eri_build()
+        G_pageable = b.build_g(D)
+        Dp, Gp = b.pinned_matrix(), b.pinned_matrix()
+        Dp[...] = D
+        Gp[...] = np.nan
+        assert b.build_g(Dp, out=Gp) is Gp
+        G_mixed = b.build_g(Dp)  # pinned in, pageable out
+        want = oracle_g(fb, D)
+        for G in (Gp, G_mixed):
+            assert np.max(np.abs(G - G_pageable)) <= 1e-13  # FP64 atomics: same sums, order differs from run to run
+            assert np.max(np.abs(G - want)) <= 1e-9
+        with pytest.raises(ValueError):
+            b.build_g(Dp, out=np.empty((fb.n_basis, fb.n_basis)))  # row-major out
+
+
+def test_spatial_and_diagonal_pair_orders_agree(monkeypatch):
+    """The pair order of the sublists (spatial order + CSR of the surviving quartets by default; FOCK_PAIR_ORDER=diag = sorted by
+    the largest diagonal integral, survivors of a row are a prefix) only changes which lane evaluates which quartet: both
+    enumerate exactly the quartets the reference's cut keeps (same counts) and give the oracle's G."""
+    fb = flat_for("w4", "6-31G**")
+    D = random_symmetric_density(fb.n_basis, seed=11)
+    want = oracle_g(fb, D)
+    res = {}
+    for order in ("spatial", "diag"):
+        monkeypatch.setenv("FOCK_PAIR_ORDER", order)
+        for bits in (("0", "4") if order == "spatial" else ("4",)):
+            monkeypatch.setenv("FOCK_ORDER_BUCKET_BITS", bits)
+            with FockBuilder(fb, storage=_lib.STORAGE_DIRECT) as b:
+                b.eri_build()
+                G = b.build_g(D)
+                res[(order, bits)] = (G, b.stats()["shell_quartets_evaluated"])
+    counts = {v[1] for v in res.values()}
+    assert len(counts) == 1, res.keys()
+    for G, _ in res.values():
+        assert np.max(np.abs(G - want)) <= 1e-9

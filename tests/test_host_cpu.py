@@ -23,7 +23,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.fock_abi_version() == 4
+    assert lib.fock_abi_version() == 5
     assert lib.fock_packed_len(7) == 406 and lib.fock_packed_len(66) == 2445366
 
 
