@@ -48,8 +48,10 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "w32cc"
 DIRECT_BY_DEFAULT = ("alkane40", "w32", "w32cc")
 # (workload, storage, mode) measured beside the headline with the same keys
-SECONDARY = [("w32cc", "direct", "accurate"), ("w32", "direct", "faithful"), ("alkane40", "direct", "faithful"),
-             ("w16", "incore", "faithful"), ("benzene", "incore", "faithful")]
+# (workload, storage, Boys mode, screening); the last entry is the like-for-like UNSCREENED number SURVEY section 8(d) rule (ii) asks for:
+# every unique shell quartet evaluated, no cut, so value = evaluated quartets / s
+SECONDARY = [("w32cc", "direct", "accurate", None), ("w32", "direct", "faithful", None), ("alkane40", "direct", "faithful", None),
+             ("w16", "incore", "faithful", None), ("benzene", "incore", "faithful", None), ("w16", "direct", "faithful", "off")]
 METRIC = "ERI+Fock-build unique shell quartets/s per SCF iteration (ms_per_step = ERI+Fock-build time per SCF iteration)"
 
 
@@ -330,16 +332,17 @@ def run_reference(args):
     emit(line)
 
 
-def config_dict(args, flat, workload=None, storage=None, mode=None):
+def config_dict(args, flat, workload=None, storage=None, mode=None, screen=None):
     workload = workload or args.workload
     storage = storage or args.storage
     mode = mode or args.mode
+    screen = screen or args.screen
     return {
         "workload": WORKLOADS[workload][0],
         "n_basis": flat.n_basis,
         "storage": storage,
         "mode": mode,
-        "screening": "reference 1e-6 cut (basis/src/electron_tensor.rs:134-155)" if args.screen == "ref" else "off",
+        "screening": "reference 1e-6 cut (basis/src/electron_tensor.rs:134-155)" if screen == "ref" else "off (every unique shell quartet evaluated)",
         "l2": ("inputs larger than L2 (packed supermatrix streamed every step)" if (flat.n_basis >= 150 and storage == "incore")
                else "L2 flushed between timed steps (256 MiB write, outside the timed region)"),
         "parallelism": (f"shell-quartet tiles sharded over {args.gpus} rank(s); one NCCL all-reduce of G per step inside fock_build_g"
@@ -385,8 +388,9 @@ class Env:
         return tuple(float(x) for x in t)
 
 
-def bench_config(env, args, workload, storage, mode, steps, warmup, clocks_for=None):
+def bench_config(env, args, workload, storage, mode, steps, warmup, clocks_for=None, screen=None):
     """Measures one configuration: device-resident steps, host-buffer (e2e) steps, roofline, parity against the golden G."""
+    screen = screen or args.screen
     torch = env.torch
     from fock_rs_b200 import _lib
     from fock_rs_b200.fock import FockBuilder
@@ -395,7 +399,7 @@ def bench_config(env, args, workload, storage, mode, steps, warmup, clocks_for=N
     n = flat.n_basis
     nq, nshell = unique_shell_quartets(flat)
     c_mode = _lib.MODE_FAITHFUL if mode == "faithful" else _lib.MODE_ACCURATE
-    c_screen = _lib.SCREEN_REFERENCE if args.screen == "ref" else _lib.SCREEN_OFF
+    c_screen = _lib.SCREEN_REFERENCE if screen == "ref" else _lib.SCREEN_OFF
     direct = storage == "direct"
     b = FockBuilder(flat, mode=c_mode, screen=c_screen, storage=_lib.STORAGE_DIRECT if direct else _lib.STORAGE_INCORE, device=env.local,
                     rank=env.rank, world=env.world, keep_eri=False, incore_shard=1 if args.incore_shard == "build" else 0)
@@ -458,7 +462,7 @@ def bench_config(env, args, workload, storage, mode, steps, warmup, clocks_for=N
     ms_step, ms_e2e = t_dev_ms / steps, t_host_ms / steps
     torch.cuda.synchronize()
     agree = float(np.max(np.abs(G.cpu().numpy().T - g_host)))
-    want = golden_g(workload, mode) if args.screen == "ref" else None
+    want = golden_g(workload, mode) if screen == "ref" else None
     parity = None if want is None else float(np.max(np.abs(g_host - want)))
     fp64_peak = b.measure_fp64_peak()
     hbm_peak, peak_src = measured_peaks()
@@ -522,7 +526,7 @@ def bench_config(env, args, workload, storage, mode, steps, warmup, clocks_for=N
         out = {
             "metric": METRIC, "value": nq / (ms_step * 1e-3), "unit": "shell_quartets/s", "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, flat, workload, storage, mode),
+            "config": config_dict(args, flat, workload, storage, mode, screen),
             "e2e": {"value": nq / (ms_e2e * 1e-3), "unit": "shell_quartets/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": 8 * n * n * world, "d2h_bytes_per_step": 8 * n * n * world},
             "gpu_launches": int((st["launches_g"] if direct else st["launches_build"] + st["launches_g"]) * steps),
             "roofline": roof_g if (dominant == "g_ms" and not direct) else roof_eri,
@@ -548,9 +552,9 @@ def run_ours(args):
     line = bench_config(env, args, args.workload, args.storage, args.mode, args.steps, args.warmup, clocks_for=clocks)
     others = []
     if not args.no_other_configs:
-        for wl, stor, mode in SECONDARY:  # all ranks take part (sharded runs); rank 0 reports
-            if (wl, stor, mode) != (args.workload, args.storage, args.mode):
-                others.append(bench_config(env, args, wl, stor, mode, args.secondary_steps, 3))
+        for wl, stor, mode, scr in SECONDARY:  # all ranks take part (sharded runs); rank 0 reports
+            if (wl, stor, mode, scr or args.screen) != (args.workload, args.storage, args.mode, args.screen):
+                others.append(bench_config(env, args, wl, stor, mode, args.secondary_steps, 3, screen=scr))
     if env.rank == 0:
         line["clocks"] = clocks
         line["configs"] = others
