@@ -867,7 +867,12 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
         if (mine <= 0) continue;
         // persistent blocks: enough to fill the machine, each strides over the warp tiles
         dim3 grid((unsigned)std::min<long long>((mine + kClassWarps - 1) / kClassWarps, (long long)num_sms * std::max(1, kBlocksPerSm * 128 / kClassThreads)));  // kBlocksPerSm counts 128-thread blocks
-        int l = launch_class(pl.cb, pl.ck, cl, sink, mode, grid, aux[slot % kStreams]);
+        // (FOCK_NO_HI_INCORE=1: in-core builds of the L >= 6 class pairs through the warp-per-quartet fallback, as in r01 -- A/B switch)
+        static const bool kNoHiIncore = getenv("FOCK_NO_HI_INCORE") != nullptr;
+        const int l_total = kPairClassLA[pl.cb] + kPairClassLB[pl.cb] + kPairClassLA[pl.ck] + kPairClassLB[pl.ck];
+        int l = (kNoHiIncore && std::is_same<Sink, TensorSink>::value && l_total >= 6)
+                    ? 0
+                    : launch_class(pl.cb, pl.ck, cl, sink, mode, grid, aux[slot % kStreams]);
         if (l == 0) {
             // no register-resident kernel for this class pair (total angular momentum >= 6): one warp per
             // quartet with shared-memory tables, driven by the same job / tile tables

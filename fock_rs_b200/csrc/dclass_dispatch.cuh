@@ -44,20 +44,26 @@ inline int launch_ket_range(const ClassLaunch &cl, const Sink &sink, dim3 grid, 
     }
 }
 
-// Class pairs with total angular momentum 6..8, integral-direct sink only (dclass_hi_*.cu): with ONE ket
+// Class pairs with total angular momentum 6..8 (dclass_hi_*.cu: integral-direct sink, dclass_hit_*.cu: in-core sink): with ONE ket
 // component per slice the compiler keeps only the sub-box of the R table that component reaches.  That fits
-// the register file up to (dd|pp)/(dd|ds); the (dp|dp), (dd|dp) and (dd|dd) slices run at 255 registers with
-// 3.5-8 KB of the table per thread in local memory (profiles/r01_v22_ptxas_class_kernels.md).  In-core builds
-// of these classes use the warp-per-quartet fallback.
-int launch_hi_dpdp(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
-int launch_hi_ddpp(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
-int launch_hi_ddds(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
-int launch_hi_dddp_a(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
-int launch_hi_dddp_b(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
-int launch_hi_dddd_a(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
-int launch_hi_dddd_b(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
-int launch_hi_dddd_c(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
-int launch_hi_dddd_d(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);
+// the register file up to (dd|pp)/(dd|ds); the (dp|dp), (dd|dp) and (dd|dd) slices carry part of the table per thread in local
+// memory (profiles/r01_v22_ptxas_class_kernels.md).
+#define FOCK_DECLARE_HI(name)                                                                              \
+    int name(const ClassLaunch &cl, const BlockDirectSink &sink, dim3 grid, cudaStream_t st);             \
+    int name(const ClassLaunch &cl, const TensorSink &sink, dim3 grid, cudaStream_t st);
+FOCK_DECLARE_HI(launch_hi_dpdp)
+FOCK_DECLARE_HI(launch_hi_ddpp)
+FOCK_DECLARE_HI(launch_hi_ddds)
+FOCK_DECLARE_HI(launch_hi_dddp_a)
+FOCK_DECLARE_HI(launch_hi_dddp_b)
+FOCK_DECLARE_HI(launch_hi_dddd_a)
+FOCK_DECLARE_HI(launch_hi_dddd_b)
+FOCK_DECLARE_HI(launch_hi_dddd_c)
+FOCK_DECLARE_HI(launch_hi_dddd_d)
+#undef FOCK_DECLARE_HI
+// the class engine runs plans for these two sinks only (class_launch.cu: run_plan)
+template <class Sink>
+constexpr bool kHasHiKernels = std::is_same<Sink, BlockDirectSink>::value || std::is_same<Sink, TensorSink>::value;
 
 #ifdef FOCK_DCLASS_DS
 template <class Sink>
@@ -81,7 +87,7 @@ int launch_dclass_dp(int ck, const ClassLaunch &cl, const Sink &sink, dim3 grid,
         case 2: return launch_ket_slices<2, 1, 1, 1, 0, 18, 1, 0>(cl, sink, grid, st);  // (dp|pp) 18 x 9 in 9 slices
         case 3: return launch_ket_slices<2, 1, 2, 0, 0, 18, 1, 0>(cl, sink, grid, st);  // (dp|ds) 18 x 6 in 6 slices
         case 4:  // (dp|dp): L = 6, 18 x 18 in 18 slices
-            if constexpr (std::is_same<Sink, BlockDirectSink>::value) return launch_hi_dpdp(cl, sink, grid, st);
+            if constexpr (kHasHiKernels<Sink>) return launch_hi_dpdp(cl, sink, grid, st);
             return 0;
         default: return 0;
     }
@@ -99,7 +105,7 @@ int launch_dclass_dd(int ck, const ClassLaunch &cl, const Sink &sink, dim3 grid,
             return launch_ket_slices<2, 2, 1, 0, 0, 18, 1, 0>(cl, sink, grid, st) +
                    launch_ket_slices<2, 2, 1, 0, 18, 18, 1, 0>(cl, sink, grid, st);
         default:  // (dd|pp), (dd|ds), (dd|dp), (dd|dd): L = 6, 6, 7, 8
-            if constexpr (std::is_same<Sink, BlockDirectSink>::value) {
+            if constexpr (kHasHiKernels<Sink>) {
                 if (ck == 2) return launch_hi_ddpp(cl, sink, grid, st);
                 if (ck == 3) return launch_hi_ddds(cl, sink, grid, st);
                 if (ck == 4) return launch_hi_dddp_a(cl, sink, grid, st) + launch_hi_dddp_b(cl, sink, grid, st);
