@@ -868,7 +868,7 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
         // persistent blocks: enough to fill the machine, each strides over the warp tiles
         dim3 grid((unsigned)std::min<long long>((mine + kClassWarps - 1) / kClassWarps, (long long)num_sms * std::max(1, kBlocksPerSm * 128 / kClassThreads)));  // kBlocksPerSm counts 128-thread blocks
         // (FOCK_NO_HI_INCORE=1: in-core builds of the L >= 6 class pairs through the warp-per-quartet fallback, as in r01 -- A/B switch)
-        static const bool kNoHiIncore = getenv("FOCK_NO_HI_INCORE") != nullptr;
+        const bool kNoHiIncore = getenv("FOCK_NO_HI_INCORE") != nullptr;  // read per build, so one process can compare both
         const int l_total = kPairClassLA[pl.cb] + kPairClassLB[pl.cb] + kPairClassLA[pl.ck] + kPairClassLB[pl.ck];
         int l = (kNoHiIncore && std::is_same<Sink, TensorSink>::value && l_total >= 6)
                     ? 0

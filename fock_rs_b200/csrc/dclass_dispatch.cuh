@@ -3,9 +3,9 @@
 // the slices compile in parallel.  A class whose n_ab x n_cd component block exceeds ~18 accumulators
 // is covered by several SLICE launches ([CB0,CB0+CBN) x [KC0,KC0+KCN)), each recomputing the Boys values
 // and the R table of its primitive quartets (cheap next to the Hermite contractions of these classes).
-// Class pairs with total angular momentum >= 6 have no such kernel (their R table alone exceeds the
-// register file of one thread): the launchers return 0 and class_launch.cu falls back to the
-// warp-per-quartet kernel of eri_shellq.cuh.
+// Every class pair up to (dd|dd) has such kernels for both sinks of the class engine (dclass_hi_*.cu / dclass_hit_*.cu hold the
+// total-angular-momentum >= 6 ones); class_launch.cu falls back to the warp-per-quartet kernel of eri_shellq.cuh only when a
+// launcher returns 0 (FOCK_NO_HI_INCORE, or a sink without instantiations).
 #pragma once
 #include <type_traits>
 

@@ -194,3 +194,25 @@ def test_spatial_and_diagonal_pair_orders_agree(monkeypatch):
     assert len(counts) == 1, res.keys()
     for G, _ in res.values():
         assert np.max(np.abs(G - want)) <= 1e-9
+
+
+def test_incore_high_l_register_kernels_match_the_warp_per_quartet_fallback(monkeypatch):
+    """In-core builds of the class pairs with total angular momentum >= 6 ((dp|dp) ... (dd|dd)) run register-resident slice
+    kernels (dclass_hit_*.cu); FOCK_NO_HI_INCORE=1 sends them through the warp-per-quartet kernel as r01 did.  Same packed
+    tensor (1e-12: two evaluation schemes of the same sums) and the oracle's G from both."""
+    fb = flat_for("ethene", "6-31G**")  # two d shells: every class pair up to (dd|dd) between different shells
+    D = random_symmetric_density(fb.n_basis, seed=13)
+    want = oracle_g(fb, D)
+    out = {}
+    for key, env in (("register", None), ("fallback", "1")):
+        if env is None:
+            monkeypatch.delenv("FOCK_NO_HI_INCORE", raising=False)
+        else:
+            monkeypatch.setenv("FOCK_NO_HI_INCORE", env)
+        with FockBuilder(fb, storage=_lib.STORAGE_INCORE, keep_eri=True) as b:
+            b.eri_build()
+            out[key] = (b.eri_export_packed(), b.build_g(D), b.stats()["launches_build"])
+    assert out["register"][2] > out["fallback"][2]  # the slice launches are there
+    assert np.max(np.abs(out["register"][0] - out["fallback"][0])) <= 1e-12
+    for key in out:
+        assert np.max(np.abs(out[key][1] - want)) <= 1e-9
