@@ -50,7 +50,7 @@ def count_surviving(diag, thr=1e-6):
     d = np.sort(np.where(np.isfinite(diag) & (diag > 0), diag, 0.0))[::-1]
     n = d.size
     asc = d[::-1]
-    with np.errstate(divide="ignore", invalid="ignore"):
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):  # denormal diagonals: thr^2 / d overflows to inf, which is the right answer
         need = np.where(d > 0, (thr * thr) / np.where(d > 0, d, 1.0), np.inf)
     cnt = n - np.searchsorted(asc, need, side="right")  # first guess: partners of entry i are the prefix [0, cnt[i])
     for _ in range(4):  # settle the boundary with the exact test (monotone in the sorted order)
