@@ -7,7 +7,8 @@ from fock_rs_b200 import _lib
 from fock_rs_b200.scf import try_scf_device
 from helpers import atoms_for
 
-for mol, basis, storage in [("water", "6-31G", 0), ("benzene", "6-31G", 0), ("w16", "6-31G", 0), ("w16", "6-31G", 1), ("alkane40", "6-31G", 1)]:
+for mol, basis, storage in [("water", "6-31G", 0), ("benzene", "6-31G", 0), ("w16", "6-31G", 0), ("w16", "6-31G", 1), ("alkane40", "6-31G", 1),
+                            ("w16", "6-31G**", 0), ("w32", "6-31G**", 1)]:  # d shells: in-core at 400 bf (25.7 GB supermatrix), direct at 800 bf
     atoms = atoms_for(mol, basis)
     with torch.cuda.stream(torch.cuda.Stream()):
         try_scf_device(atoms_for("water", "STO-3G"), 50, 1e-6, 0)  # warm up cuSOLVER/cuBLAS handles
