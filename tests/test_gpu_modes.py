@@ -216,3 +216,27 @@ def test_incore_high_l_register_kernels_match_the_warp_per_quartet_fallback(monk
     assert np.max(np.abs(out["register"][0] - out["fallback"][0])) <= 1e-12
     for key in out:
         assert np.max(np.abs(out[key][1] - want)) <= 1e-9
+
+
+@pytest.mark.parametrize("storage", [_lib.STORAGE_INCORE, _lib.STORAGE_DIRECT], ids=["incore", "direct"])
+@pytest.mark.parametrize("xyz,basis", [("H 0 0 0", "STO-3G"), ("H 0 0 0\nH 0 0 50.0", "STO-3G"), ("H 0 0 0\nH 0 0 50.0", "6-31G**"),
+                                        ("O 0 0 0", "6-31G**")],
+                         ids=["one-function", "two-far-atoms", "two-far-atoms-p", "one-atom-spd"])
+def test_degenerate_plans(xyz, basis, storage):
+    """Plans at the edges of the CSR construction: a single basis function (one pair, one quartet, which is a diagonal one),
+    two atoms 50 A apart (every cross pair falls under the cut: rows without survivors, jobs without tiles), one atom with s, p and d
+    shells (every class pair present, all on one centre)."""
+    from fock_rs_b200.basis_set import BasisSet, flatten, molecule_basis
+    from fock_rs_b200.xyz import parse_xyz
+
+    fb = flatten(molecule_basis(tuple(parse_xyz(xyz, BasisSet.named(basis)))))
+    D = random_symmetric_density(fb.n_basis, seed=3)
+    want = oracle_g(fb, D)
+    with FockBuilder(fb, storage=storage) as b:
+        b.eri_build()
+        G = b.build_g(D)
+    assert np.max(np.abs(G - want)) <= 1e-9
+    with FockBuilder(fb, storage=storage, screen=_lib.SCREEN_SCHWARZ, tau=0.5) as b:  # a cut that leaves (almost) nothing but the diagonal
+        b.eri_build()
+        G_cut = b.build_g(D)
+    assert np.all(np.isfinite(G_cut)) and np.max(np.abs(G_cut - G_cut.T)) <= 1e-12
