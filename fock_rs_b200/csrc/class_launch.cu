@@ -866,7 +866,14 @@ int ClassEngine::run_plan(const Sink &sink, std::string &err) {
         const long long mine = (pl.total_tiles - plan_rank + plan_world - 1) / plan_world;  // warp tiles of this rank
         if (mine <= 0) continue;
         // persistent blocks: enough to fill the machine, each strides over the warp tiles
-        dim3 grid((unsigned)std::min<long long>((mine + kClassWarps - 1) / kClassWarps, (long long)num_sms * std::max(1, kBlocksPerSm * 128 / kClassThreads)));  // kBlocksPerSm counts 128-thread blocks
+        // every block stages its own copy of the Boys tables (17-34 KB): a launch with few tiles gets fewer blocks, at least
+        // kTilesPerWarp tiles per warp once there is a block per SM (FOCK_TILES_PER_WARP; measured 1 / 2 / 4 / 8: 2 is 1-4 % ahead on
+        // (H2O)32/6-31G** and on an emulated 1/8 share, 4 and 8 lose -- profiles/r02/variants_call27.log)
+        static const long long kTilesPerWarp = getenv("FOCK_TILES_PER_WARP") ? std::max(1, atoi(getenv("FOCK_TILES_PER_WARP"))) : 2;
+        const long long full = (long long)num_sms * std::max(1, kBlocksPerSm * 128 / kClassThreads);
+        long long nblocks = (mine + kClassWarps - 1) / kClassWarps;
+        if (kTilesPerWarp > 1 && nblocks > num_sms) nblocks = std::max<long long>(num_sms, (mine + kClassWarps * kTilesPerWarp - 1) / (kClassWarps * kTilesPerWarp));
+        dim3 grid((unsigned)std::min<long long>(nblocks, full));  // kBlocksPerSm counts 128-thread blocks
         // (FOCK_NO_HI_INCORE=1: in-core builds of the L >= 6 class pairs through the warp-per-quartet fallback, as in r01 -- A/B switch)
         const bool kNoHiIncore = getenv("FOCK_NO_HI_INCORE") != nullptr;  // read per build, so one process can compare both
         const int l_total = kPairClassLA[pl.cb] + kPairClassLB[pl.cb] + kPairClassLA[pl.ck] + kPairClassLB[pl.ck];
